@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""Benchmark of the PCGmix+ hot path (BASELINE.json: augmented cardiac cycles/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A *step* is one pass of the hot path over one batch of synthetic cycles.  Workload at every N:
+BASELINE config 2 — ``durmixmagwarp(0.2,4)`` (PCGmix+, fused mix + magnitude warp) on a batch of
+4096 cycles x 4 channels x 2500 samples per GPU (weak scaling: every rank owns its own batches,
+pairing is drawn inside each batch exactly like the reference does, no collective on the
+augmentation path).
+
+Numbers on the JSON line
+  value ........ whole-job cycles/s with the batches already resident in HBM and the per-step
+                 draws (frames, pairing, order, knots) already uploaded: K kernel launches
+                 between two CUDA events on the launching stream, max over ranks
+  roofline ..... algorithmic bytes per launch 4*C*(2*L*B + sum_b M_b) over the mean launch time,
+                 against the measured HBM copy peak in MEASURED_PEAKS.json
+  e2e .......... the same metric through the public ``augmentations.augment`` call with HOST
+                 buffers: pinned host batch -> device, host draws, kernel, result -> pinned host,
+                 all inside the timed region
+  cpu_baseline . the CPU oracle (a port of the reference's Python loop + SciPy splines) timed on
+                 this box's host cores on a bounded sample of the same workload
+
+``--impl reference`` times only that CPU port (the reference itself is Python and is not
+available on the GPU box), spread over all host cores, and prints the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "augmented_cardiac_cycles_per_sec"
+UNIT = "cycles/s"
+METHOD = "durmixmagwarp(0.2,4)"
+WORKLOAD = "cfg2: durmixmagwarp(0.2,4) PCGmix+ on 4096 cycles x 4 ch x 2500 samples (fp32) per GPU"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--channels", type=int, default=4)
+    ap.add_argument("--length", type=int, default=2500)
+    ap.add_argument("--method", default=METHOD)
+    ap.add_argument("--resident-batches", type=int, default=4, help="distinct input batches kept in HBM per rank")
+    ap.add_argument("--e2e-steps", type=int, default=12)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-order", action="store_true", help="visit cycles in index order instead of pairing-chain order")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic workload
+# ----------------------------------------------------------------------------------------------
+def make_batch(seed: int, batch: int, channels: int, length: int):
+    from pcgmix_b200 import synth
+    rng = np.random.default_rng(seed)
+    frames = synth.cycle_frames(rng, batch, fs=1000, limit=length)
+    data = synth.cycle_signals(rng, frames, (channels,), length)
+    labels = rng.integers(0, 2, batch)
+    return data, frames, labels
+
+
+class _Args:
+    def __init__(self, method, batch):
+        self.method, self.batch_size, self.sample_rate, self.num_classes = method, batch, 1000, 2
+
+
+class _Step:
+    def __init__(self, count):
+        self.count = count
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline (oracle port), optionally spread over processes
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(payload):
+    """Run the oracle's per-cycle loop (mix + SciPy magnitude warp) on a slice of a batch."""
+    x1, x2, f1, f2, lam32, knots = payload
+    from oracle import pcgmix_oracle as orc
+    out = np.zeros_like(x1)
+    lam = np.float32(lam32)
+    for i in range(x1.shape[0]):
+        out[i] = orc.mix_pair(x1[i], x2[i], f1[i], f2[i], lam)
+    if knots is not None:
+        out = np.transpose(orc.magnitude_warp(np.transpose(out, (0, 2, 1)), knots), (0, 2, 1))
+    return out
+
+
+def cpu_reference_step(method, data, frames, labels, step, pool, workers):
+    """One step of the CPU port on host arrays; draws exactly as the reference; the per-cycle
+    work is split over ``workers`` processes when a pool is given."""
+    from oracle import pcgmix_oracle as orc
+    if pool is None:
+        out, _, _, _ = orc.augment_1d(method, data, labels, frames, step)
+        return out
+    mix = orc.same_label_mix_indices(labels, step)
+    lam32 = orc.lambda_as_float32(orc.draw_lambda(orc.parse_alpha(method, "durmixmagwarp"), step))
+    knots = None
+    if "durmixmagwarp" in method:
+        sigma, knot = orc.parse_magwarp(method)
+        knots = orc.draw_knots(data.shape[0], knot, data.shape[1], sigma)
+    partners = data[mix]
+    pframes = frames[mix]
+    bounds = np.linspace(0, data.shape[0], workers + 1).astype(int)
+    jobs = [(data[a:b], partners[a:b], frames[a:b], pframes[a:b], lam32, None if knots is None else knots[a:b])
+            for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    return np.concatenate(list(pool.map(_cpu_worker, jobs)), axis=0)
+
+
+def time_cpu_baseline(method, batch, channels, length, seconds, workers, seed=7):
+    """Cycles/s of the CPU port on a bounded sample: batches of ``batch`` cycles until ``seconds``."""
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    data, frames, labels = make_batch(seed, batch, channels, length)
+    pool = ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) if workers > 1 else None
+    try:
+        if pool is not None:
+            list(pool.map(_cpu_worker, [(data[:2], data[:2], frames[:2], frames[:2], 0.5, None)] * workers))  # start workers
+        cpu_reference_step(method, data[: max(8, workers)], frames[: max(8, workers)], labels[: max(8, workers)], 0, pool, workers)
+        done, t0, per_step = 0, time.perf_counter(), []
+        step = 1
+        while True:
+            t1 = time.perf_counter()
+            cpu_reference_step(method, data, frames, labels, step, pool, workers)
+            per_step.append(time.perf_counter() - t1)
+            done += batch
+            step += 1
+            if time.perf_counter() - t0 >= seconds:
+                break
+        elapsed = time.perf_counter() - t0
+    finally:
+        if pool is not None:
+            pool.shutdown()
+    return done / elapsed, done, elapsed, per_step
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin=None, t_end=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ts, line in self.lines:
+            if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.15):
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = os.cpu_count() or 1
+    sample = min(args.batch, 1024)
+    data, frames, labels = make_batch(7, sample, args.channels, args.length)
+    from concurrent.futures import ProcessPoolExecutor
+    import multiprocessing as mp
+    pool = ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) if workers > 1 else None
+    try:
+        if pool is not None:
+            list(pool.map(_cpu_worker, [(data[:2], data[:2], frames[:2], frames[:2], 0.5, None)] * workers))
+        for w in range(args.warmup):
+            cpu_reference_step(args.method, data, frames, labels, w, pool, workers)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            cpu_reference_step(args.method, data, frames, labels, args.warmup + k, pool, workers)
+        elapsed = time.perf_counter() - t0
+    finally:
+        if pool is not None:
+            pool.shutdown()
+    value = sample * args.steps / elapsed
+    sample_txt = (f"{args.steps} steps x {sample} cycles x {args.channels} ch x {args.length} samples of the same "
+                  f"workload (the full step is {args.batch} cycles; throughput of the per-cycle loop is flat in B)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 mix, f64 spline",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "method": args.method, "sample": sample_txt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from pcgmix_b200 import augmentations, draws, native, spline, staging, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    native.load()
+
+    B, C, L = args.batch, args.channels, args.length
+    K, W = args.steps, args.warmup
+    plan = draws.parse_method_1d(args.method)
+    magwarp = plan.branch == "durmixmagwarp"
+
+    # ---- resident inputs: NB distinct batches per rank (>> L2), per-step draws pre-uploaded -----
+    NB = max(1, args.resident_batches)
+    batches = []
+    for i in range(NB):
+        data, frames, labels = make_batch(synth.BENCH_SEED + 1000 * rank + i, B, C, L)
+        batches.append((data, frames, labels))
+    dev_data = [torch.from_numpy(b[0]).to(dev) for b in batches]
+    outs = [torch.empty_like(dev_data[0]) for _ in range(2)]
+    steps_meta = []
+    for s in range(W + K):
+        data, frames, labels = batches[s % NB]
+        seed = rank * (W + K) + s                       # the "training step" of this batch
+        mix = draws.same_label_pairing(labels, seed)
+        lam32, oml = draws.lambda_pair_fp32(draws.draw_lambda(plan.alpha, seed))
+        arrays = [frames.astype(np.int32), mix.astype(np.int32),
+                  np.arange(B, dtype=np.int32) if args.no_order else draws.processing_order(mix)]
+        if magwarp:
+            arrays.append(draws.draw_knots(B, plan.knot, C, plan.sigma))
+        on_dev = staging.upload(arrays, dev)
+        steps_meta.append({"dev": on_dev, "lam": (lam32, oml), "M": synth.mixed_samples(frames, mix)})
+    torch.cuda.synchronize()
+
+    def launch(s):
+        m = steps_meta[s]
+        augmentations.pcgmix_on_device(dev_data[s % NB], m["dev"][0], m["dev"][1], m["lam"][0], m["lam"][1],
+                                       m["dev"][3] if magwarp else None, plan.knot, order_dev=m["dev"][2],
+                                       out=outs[s % 2])
+
+    for s in range(W):
+        launch(s)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    stream = torch.cuda.current_stream(dev)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    launches_before = native.launch_count
+    t_begin = time.perf_counter()
+    marks[0].record(stream)
+    for k in range(K):
+        launch(W + k)
+        marks[k + 1].record(stream)
+    torch.cuda.synchronize()
+    t_end = time.perf_counter()
+    gpu_launches = native.launch_count - launches_before
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    total_ms = marks[0].elapsed_time(marks[K])
+    per_launch_ms = [marks[k].elapsed_time(marks[k + 1]) for k in range(K)]
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = world * K * B / (max_ms * 1e-3)
+
+    # ---- roofline of the fused kernel (rank 0's launches) ---------------------------------------
+    bytes_per_launch = [4.0 * C * (2.0 * L * B + steps_meta[W + k]["M"]) for k in range(K)]
+    mean_launch_s = statistics.fmean(per_launch_ms) * 1e-3
+    achieved = statistics.fmean(bytes_per_launch) / mean_launch_s / 1e9
+    peak, peak_src = measured_peak()
+
+    # ---- end to end through the public augment() with host buffers ------------------------------
+    E = max(3, min(args.e2e_steps, K))
+    host_in = [torch.from_numpy(b[0]).pin_memory() for b in batches[: min(NB, 2)]]
+    host_out = [torch.empty_like(host_in[0]).pin_memory() for _ in range(2)]
+    frames_t = [torch.from_numpy(b[1]) for b in batches[: min(NB, 2)]]
+    ohe_t = [torch.nn.functional.one_hot(torch.from_numpy(b[2]), 2).to(dev) for b in batches[: min(NB, 2)]]
+    wav = ["a0001"] * B
+    a = _Args(args.method, B)
+
+    def e2e_step(i, seed):
+        j = i % len(host_in)
+        d = host_in[j].to(dev, non_blocking=True)
+        out, _, _, _ = augmentations.augment(a, d, ohe_t[j], frames_t[j], wav, _Step(seed), None, dev, None)
+        host_out[i % 2].copy_(out, non_blocking=True)
+
+    for i in range(3):
+        e2e_step(i, 10_000 + i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches_e2e0 = native.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    wall0 = time.perf_counter()
+    e0.record(stream)
+    for i in range(E):
+        e2e_step(i, 20_000 + rank * E + i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    e2e_ms = max(e0.elapsed_time(e1), wall_ms)          # host work is part of the step: take the longer clock
+    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * E * B / (float(te.item()) * 1e-3)
+    e2e_launches = native.launch_count - launches_e2e0
+    in_bytes = B * C * L * 4
+    small_bytes = B * 5 * 4 + B * 4 * 2 + (B * (plan.knot + 2) * C * 8 if magwarp else 0)
+
+    # ---- CPU baseline on rank 0 at N=1 ----------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        workers = os.cpu_count() or 1
+        sample_b = 1024
+        v, done, elapsed, _ = time_cpu_baseline(args.method, sample_b, C, L, args.cpu_seconds, workers)
+        cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+               "sample": f"{done} cycles ({done // sample_b} steps of {sample_b} x {C} ch x {L}) in {elapsed:.1f} s; "
+                         f"oracle port of the reference loop, per-cycle work spread over {workers} processes"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 mix, f64 spline", "data": "synthetic",
+            "config": {"workload": WORKLOAD if (B, C, L, args.method) == (4096, 4, 2500, METHOD) else
+                       f"{args.method} on {B} cycles x {C} ch x {L} samples per GPU",
+                       "method": args.method, "cycles_per_step_per_gpu": B, "channels": C, "samples": L,
+                       "resident_input_batches": NB,
+                       "l2_policy": f"inputs larger than L2: {NB} x {in_bytes / 1e6:.0f} MB input batches + 2 output "
+                                    "buffers rotate, every step reads/writes ~330 MB",
+                       "cycle_order": "index" if args.no_order else "pairing-chain",
+                       "sharding": "batches per rank, pairing inside each batch, no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": statistics.fmean(bytes_per_launch),
+                         "kernel_ms_mean": statistics.fmean(per_launch_ms), "kernel_ms_median": statistics.median(per_launch_ms),
+                         "kernel_ms_min": min(per_launch_ms)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "steps": E, "ms_per_step": float(te.item()) / E,
+                    "h2d_bytes_per_step": in_bytes + small_bytes, "d2h_bytes_per_step": in_bytes + B * 8,
+                    "api": "pcgmix_b200.augmentations.augment (host draws + 1 kernel), pinned host in/out"},
+            "gpu_launches": gpu_launches, "gpu_launches_e2e": e2e_launches,
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,158 @@
+/*
+ * pcgmix_b200.h — C ABI of the B200-native PCGmix augmentation hot path.
+ *
+ * Everything here is `extern "C"`, takes plain DEVICE pointers + sizes + an explicit CUDA
+ * stream, never allocates, never synchronises and never calls back into the host.  Return
+ * value: 0 = launched, non-zero = argument or CUDA error (text via pcgmix_last_error()).
+ *
+ * Each entry point names the reference code it replaces (paths are into the upstream
+ * PCGmix-EXTENDED tree):
+ *
+ *   pcgmix_mix1d ............ the per-cycle loop of `augment` for 'durratiomixup'
+ *                             (augmentations.py:969-977) calling
+ *                             mixup_keepdur_multidim_tensors (augmentations.py:289-304)
+ *   pcgmix_mix1d_magwarp .... the same loop for 'durmixmagwarp' (augmentations.py:902-914)
+ *                             fused with magnitude_warp (augmentations.py:674-683, called
+ *                             at :924-928 through a device->host->device round trip)
+ *   pcgmix_mix2d ............ the spectrogram loop (augmentations2d.py:419-426) calling
+ *                             mixup_keepdur_multidim_tensors (augmentations2d.py:206-221);
+ *                             the optional zero box covers durmixtimemask / durmixfreqmask /
+ *                             durmixcutout (augmentations2d.py:286-395)
+ *   pcgmix_segment_dense .... dense per-sample Springer states -> transitions -> complete
+ *                             cycles -> frames[5] (databuilder.ipynb:593-606, cell 14)
+ *   pcgmix_segment_table .... (position, state) transition table -> cycles
+ *                             (databuilder.ipynb:928-948 cell 25; :370,:399 cell 6 when
+ *                             spec_cols > 0)
+ *   pcgmix_cut_cycles ....... cut each cycle out of its recording and zero-pad to L
+ *                             (databuilder.ipynb:627-632, :973-978; :403-411)
+ *   pcgmix_duration_features  per-cycle durations, BPM and duration ratios
+ *                             (classical.py:245-283)
+ *
+ * Host draws (probability gate, pairing, lambda, spline knots) are NOT part of this ABI:
+ * they are made on the host from the reference's seed rule and passed in, so both
+ * implementations consume identical randomness.
+ */
+#ifndef PCGMIX_B200_H_
+#define PCGMIX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCGMIX_B200_VERSION 100
+
+/* bits OR-ed into *err_flag (device int32, may be NULL) by the kernels */
+#define PCGMIX_ERR_BAD_PARTNER   1   /* mix[b] outside [0,B): cycle copied unmixed          */
+#define PCGMIX_ERR_BAD_FRAMES    2   /* frames not monotone / outside [0,P]: state skipped    */
+#define PCGMIX_ERR_BAD_PATTERN   4   /* S1 followed by something other than sys,S2,dia        */
+#define PCGMIX_ERR_OVERFLOW      8   /* more cycles/transitions than the output can hold      */
+#define PCGMIX_ERR_ZERO_DIVISION 16  /* duration ratio with a zero denominator                */
+
+#define PCGMIX_MAX_KNOT 30           /* largest `knot` of durmixmagwarp(sigma,knot) supported */
+
+/* state codes used by the segmentation entry points */
+#define PCGMIX_STATE_S1       1
+#define PCGMIX_STATE_SYSTOLE  2
+#define PCGMIX_STATE_S2       3
+#define PCGMIX_STATE_DIASTOLE 4
+#define PCGMIX_STATE_NOISE    5
+
+typedef void* pcgmix_stream_t;       /* a cudaStream_t / CUstream */
+
+int pcgmix_version(void);
+const char* pcgmix_last_error(void); /* thread-local, valid until the next failing call */
+/* SM count and compute capability of the current device (for grid sizing by callers). */
+int pcgmix_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/*
+ * PCGmix on time series.
+ *   x, out ....... [B][C][L] fp32, contiguous, must not alias
+ *   frames ....... int32, row b at frames + b*frame_stride: the five cumulative state offsets
+ *                  (S1, systole, S2, diastole starts, next-S1) of cycle b.  frame_stride is 5
+ *                  for a packed [B][5] array, 8 (with frames = cycles + 3) for the cycle table
+ *                  written by pcgmix_segment_dense/_table
+ *   mix .......... [B] int32: partner cycle of every cycle
+ *   order ........ [B] int32 or NULL: processing order of the cycles (a permutation of 0..B-1);
+ *                  changes nothing in the result, only which cycles are in flight together
+ *   lam, one_minus_lam  fp32 lambda and fp32(1)-lambda as rounded by the caller
+ * out[b,c,t] = x[b,c,t]*lam + x[mix[b],c,f2[s]+(t-f1[s])]*one_minus_lam for t inside the
+ * first min(len1_s,len2_s) samples of state s, else x[b,c,t]; mul, mul, add each rounded
+ * to fp32 (no FMA contraction), exactly like the reference's tensor expression.
+ */
+int pcgmix_mix1d(const float* x, float* out, const int32_t* frames, int32_t frame_stride,
+                 const int32_t* mix, const int32_t* order, float lam, float one_minus_lam,
+                 int32_t B, int32_t C, int32_t L, int32_t* err_flag, pcgmix_stream_t stream);
+
+/*
+ * PCGmix+ : the mix above, multiplied in the same pass by a per-(cycle,channel) cubic spline.
+ *   knots ........ [B][K+2][C] fp64, the reference's N(1,sigma) draw, in the drawn layout
+ *   coefmat ...... [(K+1)*4][K+2] fp64: linear map knots -> piecewise-cubic coefficients of
+ *                  the not-a-knot spline, row (k*4+i) = coefficient of dt^(3-i) on piece k
+ *   knot_pos ..... [K+2] fp64: np.linspace(0, L-1, K+2)
+ * out = fp32( fp64(mixed) * spline(t) ), like the reference's float64 product stored to fp32.
+ */
+int pcgmix_mix1d_magwarp(const float* x, float* out, const int32_t* frames, int32_t frame_stride,
+                         const int32_t* mix, const int32_t* order, float lam, float one_minus_lam,
+                         const double* knots, const double* coefmat, const double* knot_pos,
+                         int32_t K, int32_t B, int32_t C, int32_t L,
+                         int32_t* err_flag, pcgmix_stream_t stream);
+
+/*
+ * PCGmix on spectrograms: x, out are [B][Ch][F][T]; frames are in time-frame (column) units.
+ * Optional zero box applied after the mix (composites): rows f in [h1,h2) x columns
+ * t in [tbox[b][0], tbox[b][1]) are set to 0.  tbox == NULL means "all columns";
+ * h1 >= h2 disables the box.
+ */
+int pcgmix_mix2d(const float* x, float* out, const int32_t* frames, int32_t frame_stride,
+                 const int32_t* mix, const int32_t* order, float lam, float one_minus_lam,
+                 int32_t B, int32_t Ch, int32_t F, int32_t T,
+                 const int32_t* tbox, int32_t h1, int32_t h2,
+                 int32_t* err_flag, pcgmix_stream_t stream);
+
+/*
+ * Dense states -> cycles.  states [R][T] int8 in {1,2,3,4}; positions are floor-divided by
+ * `downsample` on the absolute index before the offsets are formed.  One cycle per transition
+ * into S1 that has a later S1 in the same recording.  Output rows, in (recording, time)
+ * order: cycles[i] = {recording, abs_start, abs_stop, f0..f4} (8 x int32, 16-byte aligned),
+ * abs_* in rescaled units, f0 = 0.
+ *   cycle_count .. [R+1] int32 out: row pointers — the cycles of recording r are rows
+ *                  [cycle_count[r], cycle_count[r+1]); cycle_count[R] is the total
+ *   max_cycles ... capacity of `cycles` (rows); cycles beyond it are dropped and flagged
+ * At most 8192 transitions per recording are examined (more raises PCGMIX_ERR_OVERFLOW).
+ * A transition into S1 (with a later S1) not followed by systole, S2, diastole raises
+ * PCGMIX_ERR_BAD_PATTERN where the reference raises an exception.
+ */
+int pcgmix_segment_dense(const int8_t* states, int32_t R, int32_t T, int32_t downsample,
+                         int32_t* cycles, int32_t max_cycles, int32_t* cycle_count,
+                         int32_t* err_flag, pcgmix_stream_t stream);
+
+/*
+ * Transition table -> cycles.  positions/codes are the concatenated (position, state-code)
+ * rows of R recordings; rec_offsets [R+1] delimits them.  If spec_cols > 0 the offsets are
+ * formed from round_half_even(position*spec_cols/rec_len[r]) instead of position/downsample.
+ */
+int pcgmix_segment_table(const int32_t* positions, const int8_t* codes, const int32_t* rec_offsets,
+                         int32_t R, int32_t downsample, int32_t spec_cols, const int32_t* rec_len,
+                         int32_t* cycles, int32_t max_cycles, int32_t* cycle_count,
+                         int32_t* err_flag, pcgmix_stream_t stream);
+
+/*
+ * Cut + zero-pad.  signal [R][C][T] fp32 (C bands/rows of every recording); for cycle i
+ * out[i][c][0:L] = signal[rec][c][abs_start : abs_stop] truncated/zero-filled to L.
+ * n_cycles may be read from the device (cycle_count[R]) by passing n_cycles_dev != NULL, in
+ * which case `n_cycles` is only the grid bound.
+ */
+int pcgmix_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T,
+                      const int32_t* cycles, int32_t n_cycles, const int32_t* n_cycles_dev,
+                      float* out, int32_t L, pcgmix_stream_t stream);
+
+/* 14 fp64 features per cycle from frames [n][5] int32 (stride `frame_stride` int32 between rows). */
+int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,
+                             double* features, int32_t* err_flag, pcgmix_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCGMIX_B200_H_ */

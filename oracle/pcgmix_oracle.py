@@ -141,9 +141,9 @@ def mix_pair(d1, d2, f1, f2, lam):
 
 def mix_batch(data, frames, mix_indices, lam32):
     """The reference's per-cycle loop (augmentations.py:969-977, augmentations2d.py:419-426)."""
-    import torch
-
-    is_torch = isinstance(data, torch.Tensor)
+    is_torch = type(data).__module__.split(".")[0] == "torch"
+    if is_torch:
+        import torch
     frames_np = frames.numpy() if hasattr(frames, "numpy") else np.asarray(frames)
     if is_torch:
         out = torch.zeros(tuple(data.shape), dtype=data.dtype)
@@ -242,8 +242,7 @@ def augment_1d(method: str, data, labels, frames, step: int, wav=None):
     Follows augmentations.py:864-929 (``durmixmagwarp``) and :931-981 (``durratiomixup``);
     like the reference, ``durmixmagwarp`` is tested first.
     """
-    import torch
-
+    is_torch = type(data).__module__.split(".")[0] == "torch"
     if "durmixmagwarp" in method:
         branch = "durmixmagwarp"
     elif "durratiomixup" in method:
@@ -260,11 +259,15 @@ def augment_1d(method: str, data, labels, frames, step: int, wav=None):
     knots = None
     if branch == "durmixmagwarp":
         sigma, knot = parse_magwarp(method)
-        as_np = out.detach().cpu().numpy() if isinstance(out, torch.Tensor) else out
+        as_np = out.detach().cpu().numpy() if is_torch else out
         as_np = np.transpose(as_np, (0, 2, 1))
         knots = draw_knots(as_np.shape[0], knot, as_np.shape[2], sigma)
         as_np = np.transpose(magnitude_warp(as_np, knots), (0, 2, 1))
-        out = torch.from_numpy(np.ascontiguousarray(as_np)) if isinstance(out, torch.Tensor) else as_np
+        if is_torch:
+            import torch
+            out = torch.from_numpy(np.ascontiguousarray(as_np))
+        else:
+            out = as_np
     return out, mix, lam32, knots
 
 

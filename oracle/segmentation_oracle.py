@@ -47,14 +47,14 @@ def transitions_from_dense(states: np.ndarray):
     return [int(p) for p in pos], entered
 
 
-def cycles_from_transitions(positions, codes, downsample: int = 1):
+def cycles_from_transitions(positions, codes, downsample: int = 1, noise_skip: bool = True):
     """Complete-cycle rule shared by cells 14 and 25.
 
     ``positions`` are absolute sample indices of the state changes, ``codes`` the state entered.
     Positions are floor-divided by ``downsample`` FIRST (on the absolute index), then a cycle
     starts at every transition into S1 that has another S1 somewhere later; its four states must
     read S1, systole, S2, diastole (else the reference raises), unless one of them is a noise
-    marker, in which case the cycle is skipped.  Returns ``(rel_frames (n,5) int64,
+    marker, in which case the cycle is skipped (cell 25 only: ``noise_skip``).  Returns ``(rel_frames (n,5) int64,
     abs_start (n,) int64, abs_stop (n,) int64)`` in downsampled units.
     """
     pos = [int(p) // downsample for p in positions]
@@ -63,7 +63,7 @@ def cycles_from_transitions(positions, codes, downsample: int = 1):
     for i, code in enumerate(codes):
         if code == S1 and S1 in codes[i + 1:]:
             four = codes[i:i + 4]
-            if NOISE in four:
+            if noise_skip and NOISE in four:
                 continue
             if four != [S1, SYSTOLE, S2, DIASTOLE]:
                 raise SegmentPatternError("Segment states are not correct!")
@@ -79,7 +79,7 @@ def cycles_from_transitions(positions, codes, downsample: int = 1):
 def cycles_from_dense(states: np.ndarray, downsample: int = 1):
     """Cell 14 end to end for one recording."""
     pos, entered = transitions_from_dense(states)
-    return cycles_from_transitions(pos, entered, downsample)
+    return cycles_from_transitions(pos, entered, downsample, noise_skip=False)
 
 
 def spectrogram_positions(positions, n_spec_cols: int, n_samples: int):

@@ -1,0 +1,95 @@
+"""Drop-in for the reference's ``augmentations.augment`` on the PCGmix / PCGmix+ branches.
+
+Same nine positional parameters, same 4-tuple result as ``augmentations.py:698`` of the
+reference; ``train_model.py:507`` can import this module instead of the original.  What runs
+where:
+
+  host (Python)  method-string parse, probability gate, pairing, lambda, knot draw — replayed
+                 from ``step_counter.count`` exactly like the reference (see ``draws.py``)
+  device (CUDA)  everything that touches the samples: one fused kernel launch per step
+                 (``pcgmix_mix1d`` or ``pcgmix_mix1d_magwarp`` of ``include/pcgmix_b200.h``)
+
+The reference loops over the batch in Python (``augmentations.py:969-977``) and, for PCGmix+,
+takes the batch to the host for a SciPy spline per cycle and channel and back
+(``:924-928``); here the batch never leaves the GPU and is read once and written once.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import draws, native, spline, staging
+from ._common import host_frames, labels_from_one_hot, require_cuda_batch
+
+__all__ = ["augment", "pcgmix_on_device"]
+
+_table_cache = {}
+
+
+def _device_tables(length: int, knot: int, device):
+    """knot positions and coefficient matrix as device tensors, cached per (L, knot, device)."""
+    key = (int(length), int(knot), str(device))
+    hit = _table_cache.get(key)
+    if hit is None:
+        pos, mat = spline.magwarp_tables(length, knot)
+        hit = (torch.from_numpy(np.array(pos)).to(device), torch.from_numpy(np.array(mat)).to(device))
+        if len(_table_cache) > 32:
+            _table_cache.clear()
+        _table_cache[key] = hit
+    return hit
+
+
+def pcgmix_on_device(data, frames_dev, mix_dev, lam32, one_minus_lam32, knots_dev=None, knot=None,
+                     order_dev=None, out=None, err_flag=None):
+    """Device-resident entry: everything already on the GPU (int32 frames / pairing / order,
+    float64 knots).  Launches exactly one kernel on the current stream and returns ``out``."""
+    if out is None:
+        out = torch.empty_like(data)
+    if knots_dev is None:
+        native.mix1d(data, out, frames_dev, mix_dev, lam32, one_minus_lam32, order=order_dev, err_flag=err_flag)
+    else:
+        if knot > native.MAX_KNOT:
+            raise ValueError(f"durmixmagwarp knot={knot} exceeds the supported maximum {native.MAX_KNOT}")
+        pos_dev, mat_dev = _device_tables(data.shape[2], knot, data.device)
+        native.mix1d_magwarp(data, out, frames_dev, mix_dev, lam32, one_minus_lam32, knots_dev, mat_dev,
+                             pos_dev, knot, order=order_dev, err_flag=err_flag)
+    return out
+
+
+def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RESULTS_ARGS):
+    """PCGmix (``durratiomixup``) / PCGmix+ (``durmixmagwarp(sigma,knot)``) on a (B, C, L) batch.
+
+    Returns ``(data_new, target_ohe, mix_indices, None)``; when the method is not one the
+    reference implements, or the probability gate fails, returns ``(data, target_ohe, [], None)``
+    with the very same objects (``augmentations.py:731-732, 938-939``)."""
+    plan = draws.parse_method_1d(args.method)
+    if plan is None:
+        return data, target_ohe, [], None
+    step = step_counter.count
+    if draws.gate(step) >= plan.probability:
+        return data, target_ohe, [], None
+
+    data = require_cuda_batch(data, 3, "augment")
+    batch, channels, length = data.shape
+    labels = labels_from_one_hot(target_ohe)
+    mix_indices = draws.pairing(args.method, labels, wav, step)
+    lam = draws.draw_lambda(plan.alpha, step)
+    lam32, one_minus = draws.lambda_pair_fp32(lam)
+
+    uploads = [host_frames(frames, batch, length), mix_indices.astype(np.int32),
+               draws.processing_order(mix_indices)]
+    if plan.branch == "durmixmagwarp":
+        if plan.knot > native.MAX_KNOT:
+            raise ValueError(f"durmixmagwarp knot={plan.knot} exceeds the supported maximum {native.MAX_KNOT}")
+        uploads.append(draws.draw_knots(batch, plan.knot, channels, plan.sigma))
+    on_dev = staging.upload(uploads, data.device)
+    knots_dev = on_dev[3] if plan.branch == "durmixmagwarp" else None
+    data_new = pcgmix_on_device(data, on_dev[0], on_dev[1], lam32, one_minus, knots_dev, plan.knot,
+                                order_dev=on_dev[2])
+
+    if plan.mix_all:
+        # soft labels, as augmentations.py:915-917 / :978-980
+        lams = torch.from_numpy(np.array(np.ones(batch) * lam).astype("float32")).to(data.device)
+        lams_target = lams[:, None]
+        target_ohe = target_ohe * lams_target + target_ohe[mix_indices] * (1 - lams_target)
+    return data_new, target_ohe, mix_indices, None

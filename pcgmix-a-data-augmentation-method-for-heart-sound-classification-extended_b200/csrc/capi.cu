@@ -1,0 +1,146 @@
+// extern "C" boundary of libpcgmix_b200.so — see include/pcgmix_b200.h for the contract.
+// Argument checks happen here; nothing below this file allocates or synchronises.
+
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+thread_local char g_error[512] = "";
+
+int fail(const char* what) {
+    std::snprintf(g_error, sizeof(g_error), "%s", what);
+    return 1;
+}
+
+int fail_cuda(const char* where, cudaError_t e) {
+    std::snprintf(g_error, sizeof(g_error), "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+    return 2;
+}
+
+bool mul_fits_int32(long long a, long long b) { return a * b <= 2147483647LL; }
+
+int check_mix_common(const float* x, float* out, const int32_t* frames, int32_t frame_stride, const int32_t* mix,
+                     int32_t B, int32_t R, int32_t P) {
+    if (x == nullptr || out == nullptr || frames == nullptr || mix == nullptr) return fail("null pointer argument");
+    if (x == out) return fail("x and out must not alias (partners read the original samples)");
+    if (B < 0 || R <= 0 || P <= 0) return fail("B must be >= 0 and the cycle shape positive");
+    if (frame_stride < 5) return fail("frame_stride must be >= 5");
+    if (!mul_fits_int32(R, P)) return fail("a cycle must hold fewer than 2^31 samples");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcgmix_version(void) { return PCGMIX_B200_VERSION; }
+
+const char* pcgmix_last_error(void) { return g_error; }
+
+int pcgmix_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail_cuda("cudaGetDevice", e);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, dev);
+    if (e != cudaSuccess) return fail_cuda("cudaGetDeviceProperties", e);
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+int pcgmix_mix1d(const float* x, float* out, const int32_t* frames, int32_t frame_stride, const int32_t* mix,
+                 const int32_t* order, float lam, float one_minus_lam, int32_t B, int32_t C, int32_t L,
+                 int32_t* err_flag, pcgmix_stream_t stream) {
+    if (int rc = check_mix_common(x, out, frames, frame_stride, mix, B, C, L)) return rc;
+    if (B == 0) return 0;
+    pcgmix::MixArgs a{};
+    a.x = x; a.out = out; a.frames = frames; a.frame_stride = frame_stride; a.mix = mix; a.order = order;
+    a.err = err_flag; a.lam = lam; a.one_minus_lam = one_minus_lam; a.B = B; a.R = C; a.P = L; a.F = 1;
+    const cudaError_t e = pcgmix::launch_mix(a, false, false, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix1d", e);
+}
+
+int pcgmix_mix1d_magwarp(const float* x, float* out, const int32_t* frames, int32_t frame_stride,
+                         const int32_t* mix, const int32_t* order, float lam, float one_minus_lam,
+                         const double* knots, const double* coefmat, const double* knot_pos, int32_t K, int32_t B,
+                         int32_t C, int32_t L, int32_t* err_flag, pcgmix_stream_t stream) {
+    if (int rc = check_mix_common(x, out, frames, frame_stride, mix, B, C, L)) return rc;
+    if (knots == nullptr || coefmat == nullptr || knot_pos == nullptr) return fail("null spline argument");
+    if (K < 0 || K > PCGMIX_MAX_KNOT) return fail("knot count outside [0, PCGMIX_MAX_KNOT]");
+    if (L < 2) return fail("magnitude warp needs at least two samples per row");
+    if (B == 0) return 0;
+    pcgmix::MixArgs a{};
+    a.x = x; a.out = out; a.frames = frames; a.frame_stride = frame_stride; a.mix = mix; a.order = order;
+    a.err = err_flag; a.lam = lam; a.one_minus_lam = one_minus_lam; a.B = B; a.R = C; a.P = L; a.F = 1;
+    a.knots = knots; a.coefmat = coefmat; a.knot_pos = knot_pos; a.K = K;
+    a.inv_h = static_cast<double>(K + 1) / static_cast<double>(L - 1);
+    const cudaError_t e = pcgmix::launch_mix(a, true, false, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix1d_magwarp", e);
+}
+
+int pcgmix_mix2d(const float* x, float* out, const int32_t* frames, int32_t frame_stride, const int32_t* mix,
+                 const int32_t* order, float lam, float one_minus_lam, int32_t B, int32_t Ch, int32_t F, int32_t T,
+                 const int32_t* tbox, int32_t h1, int32_t h2, int32_t* err_flag, pcgmix_stream_t stream) {
+    if (Ch <= 0 || F <= 0) return fail("Ch and F must be positive");
+    if (!mul_fits_int32(Ch, F)) return fail("Ch*F too large");
+    if (int rc = check_mix_common(x, out, frames, frame_stride, mix, B, Ch * F, T)) return rc;
+    if (B == 0) return 0;
+    pcgmix::MixArgs a{};
+    a.x = x; a.out = out; a.frames = frames; a.frame_stride = frame_stride; a.mix = mix; a.order = order;
+    a.err = err_flag; a.lam = lam; a.one_minus_lam = one_minus_lam; a.B = B; a.R = Ch * F; a.P = T;
+    a.tbox = tbox; a.F = F; a.h1 = h1 < 0 ? 0 : h1; a.h2 = h2 > F ? F : h2;
+    const bool box = a.h1 < a.h2;
+    const cudaError_t e = pcgmix::launch_mix(a, false, box, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix2d", e);
+}
+
+int pcgmix_segment_dense(const int8_t* states, int32_t R, int32_t T, int32_t downsample, int32_t* cycles,
+                         int32_t max_cycles, int32_t* cycle_count, int32_t* err_flag, pcgmix_stream_t stream) {
+    if (cycle_count == nullptr || (R > 0 && states == nullptr)) return fail("null pointer argument");
+    if (R < 0 || T < 0 || downsample < 1 || max_cycles < 0) return fail("bad size argument");
+    if (max_cycles > 0 && cycles == nullptr) return fail("null cycles with max_cycles > 0");
+    if ((reinterpret_cast<uintptr_t>(cycles) & 15u) != 0) return fail("cycles must be 16-byte aligned");
+    const cudaError_t e = pcgmix::launch_segment_dense(states, R, T, downsample, cycles, max_cycles, cycle_count,
+                                                       err_flag, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_segment_dense", e);
+}
+
+int pcgmix_segment_table(const int32_t* positions, const int8_t* codes, const int32_t* rec_offsets, int32_t R,
+                         int32_t downsample, int32_t spec_cols, const int32_t* rec_len, int32_t* cycles,
+                         int32_t max_cycles, int32_t* cycle_count, int32_t* err_flag, pcgmix_stream_t stream) {
+    if (cycle_count == nullptr || rec_offsets == nullptr) return fail("null pointer argument");
+    if (R < 0 || downsample < 1 || max_cycles < 0 || spec_cols < 0) return fail("bad size argument");
+    if (spec_cols > 0 && rec_len == nullptr) return fail("rec_len required when spec_cols > 0");
+    if (max_cycles > 0 && cycles == nullptr) return fail("null cycles with max_cycles > 0");
+    if ((reinterpret_cast<uintptr_t>(cycles) & 15u) != 0) return fail("cycles must be 16-byte aligned");
+    const cudaError_t e = pcgmix::launch_segment_table(positions, codes, rec_offsets, R, downsample, spec_cols,
+                                                       rec_len, cycles, max_cycles, cycle_count, err_flag,
+                                                       static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_segment_table", e);
+}
+
+int pcgmix_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T, const int32_t* cycles, int32_t n_cycles,
+                      const int32_t* n_cycles_dev, float* out, int32_t L, pcgmix_stream_t stream) {
+    if (n_cycles < 0 || R < 0 || C < 0 || T < 0 || L < 0) return fail("bad size argument");
+    if (n_cycles > 0 && (signal == nullptr || cycles == nullptr || out == nullptr)) return fail("null pointer argument");
+    if ((reinterpret_cast<uintptr_t>(cycles) & 15u) != 0) return fail("cycles must be 16-byte aligned");
+    const cudaError_t e = pcgmix::launch_cut_cycles(signal, R, C, T, cycles, n_cycles, n_cycles_dev, out, L,
+                                                    static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_cut_cycles", e);
+}
+
+int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs, double* features,
+                             int32_t* err_flag, pcgmix_stream_t stream) {
+    if (n < 0 || fs <= 0 || frame_stride < 5) return fail("bad size argument");
+    if (n > 0 && (frames == nullptr || features == nullptr)) return fail("null pointer argument");
+    const cudaError_t e = pcgmix::launch_duration_features(frames, frame_stride, n, fs, features, err_flag,
+                                                           static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_duration_features", e);
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Shared declarations for the PCGmix B200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pcgmix_b200.h"
+
+namespace pcgmix {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kMaxPieces = PCGMIX_MAX_KNOT + 1;   // cubic pieces of the magnitude-warp spline
+
+// Arguments of the fused gather-mix(-warp) kernel.  A "cycle" is R rows of pitch P floats,
+// contiguous (1D: R = channels, P = L samples; 2D: R = Ch*F, P = T time frames).
+struct MixArgs {
+    const float* x;
+    float* out;
+    const int32_t* frames;     // row b at frames + b*frame_stride, 5 offsets
+    int32_t frame_stride;
+    const int32_t* mix;        // [B]
+    const int32_t* order;      // [B] or nullptr
+    int32_t* err;              // device flag word or nullptr
+    float lam;
+    float one_minus_lam;
+    int32_t B;
+    int32_t R;
+    int32_t P;
+    int32_t n_per_cycle;       // R*P
+    int32_t nvec;              // vector units per cycle (n_per_cycle / VEC)
+    int32_t chunk_len;         // vector units per CTA
+    int32_t chunks_per_cycle;
+    int32_t qstep;             // blockDim*VEC = qstep*P + rstep
+    int32_t rstep;
+    // magnitude warp (PCGmix+)
+    const double* knots;       // [B][K+2][R]
+    const double* coefmat;     // [(K+1)*4][K+2]
+    const double* knot_pos;    // [K+2]
+    double inv_h;              // (K+1)/(P-1)
+    int32_t K;
+    // zero box (2D composites)
+    const int32_t* tbox;       // [B][2] or nullptr
+    int32_t F;
+    int32_t h1;
+    int32_t h2;
+};
+
+// mix_kernels.cu
+cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t stream);
+
+// segment_kernels.cu
+cudaError_t launch_segment_dense(const int8_t* states, int32_t R, int32_t T, int32_t downsample,
+                                 int32_t* cycles, int32_t max_cycles, int32_t* cycle_count,
+                                 int32_t* err, cudaStream_t stream);
+cudaError_t launch_segment_table(const int32_t* positions, const int8_t* codes, const int32_t* rec_offsets,
+                                 int32_t R, int32_t downsample, int32_t spec_cols, const int32_t* rec_len,
+                                 int32_t* cycles, int32_t max_cycles, int32_t* cycle_count,
+                                 int32_t* err, cudaStream_t stream);
+cudaError_t launch_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T, const int32_t* cycles,
+                              int32_t n_cycles, const int32_t* n_cycles_dev, float* out, int32_t L,
+                              cudaStream_t stream);
+cudaError_t launch_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,
+                                     double* features, int32_t* err, cudaStream_t stream);
+
+}  // namespace pcgmix

@@ -1,0 +1,209 @@
+"""Host-side replay of the reference's seeded draws and of its method-string mini-language.
+
+Everything random on the PCGmix path is drawn on the host from the integer training step
+(``step_counter.count``) and handed to the device kernels, so this implementation and the
+reference consume identical randomness.  The calls below are made on the *same* generators, in
+the *same* order, as the reference makes them:
+
+  gate ............ ``random.Random(step).uniform(0, 1)``            augmentations.py:936-939
+  pairing ......... per class ``random.Random(step).sample(idx, n)`` augmentations.py:500-514
+  lambda .......... ``np.random.seed(step); np.random.beta(a, a)``   augmentations.py:659-666
+  knots ........... ``np.random.normal(1, sigma, (B, knot+2, C))``   augmentations.py:677
+                    from the global legacy stream right after the beta draw
+
+The global NumPy stream is re-seeded on purpose: the reference does it every step, and code
+that runs after ``augment`` in the same process sees that state.
+"""
+from __future__ import annotations
+
+import dataclasses
+import random
+from typing import Optional, Sequence
+
+import numpy as np
+
+# Branches of the reference dispatcher that are tested BEFORE the PCGmix branches
+# (augmentations.py:734, 777, 807).  A method string that also contains one of these would never
+# reach PCGmix in the reference, so it is refused here instead of being silently reinterpreted.
+_EARLIER_1D = ("durmixrespscale", "respiratoryscale", "timemask")
+
+# Every branch keyword of the reference dispatchers (augmentations.py:700-729,
+# augmentations2d.py:269-281): a method containing none of them is returned untouched.
+METHODS_1D = ("durratiocutmix", "lengthcutmix", "datasetcutmix", "wav-durratiocutmix", "wavcutmix",
+              "lc-nointrusion", "labelcutmix", "swapsysdia", "s1s2mask", "cont-cutmix", "saliency-cutmix",
+              "latentmixup", "manifold-cutmix(ch)", "manifold-cutmix", "manifold-cutout(ch)",
+              "manifold-cutout", "cutmix(ch)", "cutmix", "cutout(ch)", "cutout", "gaussiannoise",
+              "magnitudewarp", "timewarp", "mixup", "timemask", "durratiomixup", "durmixmagwarp",
+              "respiratoryscale", "durmixrespscale")
+METHODS_2D = ("durratiocutmix", "cutmix", "mixup", "latentmixup", "freqmask", "timemask", "cutout",
+              "durratiomixup", "durmixfreqmask", "durmixtimemask", "durmixcutout")
+
+# Pairing / displacement modifiers this implementation does not provide (they need files or
+# trained models that are not part of the reference repository, or are ablations).
+_UNSUPPORTED_MODIFIERS = ("(sameCVD)", "(closestbins=", "(closestknn=", "(salopt", "(rand)")
+
+
+@dataclasses.dataclass
+class Plan1D:
+    branch: str                 # 'durratiomixup' | 'durmixmagwarp'
+    probability: float
+    alpha: float
+    sigma: float = 0.2
+    knot: int = 4
+    mix_all: bool = False
+
+
+@dataclasses.dataclass
+class Plan2D:
+    branch: str                 # 'durratiomixup' | 'durmixtimemask' | 'durmixfreqmask' | 'durmixcutout'
+    probability: float
+    time_region_max: float = 0.2
+    freq_region_max: float = 0.2
+
+
+def _probability(method: str) -> float:
+    parts = method.split("+")
+    return float(parts[-1]) if len(parts) > 1 else 1.0
+
+
+def _alpha(method: str, branch: str) -> float:
+    if len(method.split("(alpha=")) > 1:
+        return float(method.split("(alpha=")[1].split(")" + branch)[0])
+    return 1.0
+
+
+def _clamp01(v: float) -> float:
+    return min(max(v, 0), 1)
+
+
+def parse_method_1d(method: str) -> Optional[Plan1D]:
+    """Return the plan for a PCGmix(+) method string, ``None`` if the reference would return the
+    batch untouched, and raise for strings that the reference routes to another augmentation."""
+    if not any(k in method for k in METHODS_1D):
+        return None
+    for earlier in _EARLIER_1D:
+        if earlier in method:
+            raise NotImplementedError(
+                f"method {method!r} is routed to the {earlier!r} branch by the reference dispatcher; "
+                "only durratiomixup / durmixmagwarp are provided here")
+    if "durmixmagwarp" in method:
+        branch = "durmixmagwarp"
+    elif "durratiomixup" in method:
+        branch = "durratiomixup"
+    else:
+        raise NotImplementedError(f"method {method!r} is not on the PCGmix hot path")
+    for mod in _UNSUPPORTED_MODIFIERS:
+        if mod in method:
+            raise NotImplementedError(f"modifier {mod} of {method!r} is not provided by this implementation")
+    plan = Plan1D(branch=branch, probability=_probability(method), alpha=_alpha(method, branch),
+                  mix_all="(mixAll)" in method)
+    if branch == "durmixmagwarp" and len(method.split("durmixmagwarp(")) > 1:
+        plan.sigma = float(method.split("durmixmagwarp(")[1].split(",")[0])
+        plan.knot = int(method.split(",")[1].split(")")[0])
+    return plan
+
+
+def parse_method_2d(method: str) -> Optional[Plan2D]:
+    """Same for the spectrogram dispatcher (augmentations2d.py:283-427); branch order as there."""
+    if not any(k in method for k in METHODS_2D):
+        return None
+    if "durmixcutout" in method:
+        plan = Plan2D("durmixcutout", _probability(method))
+        if len(method.split("cutout(")) > 1:
+            plan.time_region_max = _clamp01(float(method.split("cutout(")[1].split(",")[0]))
+            plan.freq_region_max = _clamp01(float(method.split(",")[1].split(")")[0]))
+        return plan
+    if "durmixtimemask" in method:
+        plan = Plan2D("durmixtimemask", _probability(method))
+        if len(method.split("timemask(")) > 1:
+            plan.time_region_max = _clamp01(float(method.split("timemask(")[1].split(")")[0]))
+        return plan
+    if "durmixfreqmask" in method:
+        plan = Plan2D("durmixfreqmask", _probability(method))
+        if len(method.split("freqmask(")) > 1:
+            plan.freq_region_max = _clamp01(float(method.split("freqmask(")[1].split(")")[0]))
+        return plan
+    if "durratiomixup" in method:
+        if "(salopt" in method:
+            raise NotImplementedError("the (salopt...) variants are not provided by this implementation")
+        return Plan2D("durratiomixup", _probability(method))
+    raise NotImplementedError(f"method {method!r} is not on the PCGmix hot path")
+
+
+def gate(step: int) -> float:
+    return random.Random(step).uniform(0, 1)
+
+
+def _grouped_permutation(keys: Sequence, step: int) -> np.ndarray:
+    groups = {}
+    for i, k in enumerate(keys):
+        groups.setdefault(k, []).append(i)
+    mix = np.arange(0, len(keys), 1)
+    for members in groups.values():
+        mix[members] = random.Random(step).sample(list(mix[members]), len(members))
+    return mix
+
+
+def same_label_pairing(labels: np.ndarray, step: int) -> np.ndarray:
+    """Default pairing: a seeded permutation inside every class, classes visited in order of first
+    appearance, each from a fresh ``Random(step)`` (augmentations.py:500-514)."""
+    return _grouped_permutation(np.asarray(labels).reshape(-1).tolist(), step)
+
+
+def pairing(method: str, labels: np.ndarray, wav, step: int) -> np.ndarray:
+    """Pairing with the modifiers applied in the reference's order (augmentations.py:943-952)."""
+    labels = np.asarray(labels).reshape(-1)
+    mix = same_label_pairing(labels, step)
+    if "(samePCG)" in method:
+        mix = _grouped_permutation(list(wav), step)
+    if "(sameDataset)" in method:
+        mix = _grouped_permutation([f"{w[0]}_{t}" for w, t in zip(wav, labels.tolist())], step)
+    if "(mixAll)" in method:
+        mix = np.array(random.Random(step).sample(list(np.arange(0, len(labels), 1)), len(labels)))
+    return mix
+
+
+def draw_lambda(alpha: float, step: int) -> float:
+    if alpha > 0.0:
+        np.random.seed(step)
+        return float(np.random.beta(alpha, alpha))
+    return 1.0
+
+
+def lambda_pair_fp32(lam: float):
+    """``(lam32, 1 - lam32)`` rounded the way the reference's float32 tensor expression rounds."""
+    lam32 = np.array(np.ones(1) * lam).astype("float32")[0]
+    return lam32, np.float32(1) - lam32
+
+
+def draw_knots(batch: int, knot: int, channels: int, sigma: float) -> np.ndarray:
+    return np.random.normal(loc=1.0, scale=sigma, size=(batch, knot + 2, channels))
+
+
+def mask_geometry(step: int, region_max: float):
+    """``(gap, start_fraction)`` of the seeded zero box (augmentations2d.py:317-319, 354-356)."""
+    gap = random.Random(step + 131071).uniform(0, region_max)
+    frac1 = random.Random(step + 13119).uniform(0, 1 - gap)
+    return gap, frac1
+
+
+def processing_order(mix: np.ndarray) -> np.ndarray:
+    """Order in which the device visits the cycles: follow the pairing permutation's chains
+    (b, mix[b], mix[mix[b]], ...), so that a cycle is read as "partner" and as "itself" by CTAs
+    that are in flight together and the second read is served by L2 instead of HBM.  Any
+    permutation gives the same output; this one only changes locality."""
+    mix = np.asarray(mix, dtype=np.int64)
+    n = mix.shape[0]
+    seen = np.zeros(n, dtype=bool)
+    order = np.empty(n, dtype=np.int32)
+    k = 0
+    for start in range(n):
+        b = start
+        while not seen[b]:
+            seen[b] = True
+            order[k] = b
+            k += 1
+            b = int(mix[b])
+            if not (0 <= b < n):
+                break
+    return order

@@ -1,0 +1,261 @@
+"""ctypes binding of ``csrc/libpcgmix_b200.so`` — the C ABI declared in ``include/pcgmix_b200.h``.
+
+This is the only place where Python meets the CUDA kernels.  PyTorch is used for device
+memory and streams only: every call passes raw device pointers (``tensor.data_ptr()``) and the
+current CUDA stream handle, and the library neither allocates nor synchronises.
+
+There is no fallback: if the library is missing or a tensor is not a contiguous CUDA tensor of
+the expected dtype, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import torch
+
+from . import build_native
+
+ERR_BAD_PARTNER = 1
+ERR_BAD_FRAMES = 2
+ERR_BAD_PATTERN = 4
+ERR_OVERFLOW = 8
+ERR_ZERO_DIVISION = 16
+MAX_KNOT = 30
+
+_c_i32 = ctypes.c_int32
+_c_f32 = ctypes.c_float
+_ptr = ctypes.c_void_p
+
+# name -> argtypes; restype is int for all but pcgmix_last_error.  Mirrors include/pcgmix_b200.h
+# (tests/test_abi.py checks the two against each other).
+SIGNATURES = {
+    "pcgmix_version": [],
+    "pcgmix_last_error": [],
+    "pcgmix_device_info": [_ptr, _ptr, _ptr],
+    "pcgmix_mix1d": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _c_i32, _c_i32, _c_i32, _ptr, _ptr],
+    "pcgmix_mix1d_magwarp": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _ptr, _ptr, _ptr,
+                             _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr],
+    "pcgmix_mix2d": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _c_i32, _c_i32, _c_i32, _c_i32,
+                     _ptr, _c_i32, _c_i32, _ptr, _ptr],
+    "pcgmix_segment_dense": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr],
+    "pcgmix_segment_table": [_ptr, _ptr, _ptr, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _c_i32, _ptr, _ptr, _ptr],
+    "pcgmix_cut_cycles": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _c_i32, _ptr],
+    "pcgmix_duration_features": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
+}
+
+_lib = None
+_lock = threading.Lock()
+launch_count = 0     # kernels launched through this binding (bench.py reports it)
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return build_native.LIB_PATH
+
+
+def load(build_if_missing: bool = False):
+    """Load the shared library (once).  Raises ``NativeLibraryError`` if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = library_path()
+        if not os.path.exists(path):
+            if not build_if_missing:
+                raise NativeLibraryError(
+                    f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(needs nvcc).  There is no CPU fallback for the PCGmix kernels.")
+            build_native.build()
+        lib = ctypes.CDLL(path)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_char_p if name == "pcgmix_last_error" else ctypes.c_int
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        msg = load().pcgmix_last_error()
+        raise RuntimeError(f"{what} failed (status {rc}): {msg.decode() if msg else 'unknown error'}")
+
+
+def _dev_ptr(t, dtype, name, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError(f"{name} is required")
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor: the PCGmix kernels have no CPU path")
+    if t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+def _frames_ptr(frames):
+    """Pointer and row stride (in int32) of a frames table.  Accepts a packed (B, 5) tensor or a
+    strided view such as ``cycles[:, 3:]`` of the (n, 8) cycle table written by the segmentation
+    kernels — the kernels take the stride, no copy is made."""
+    if not isinstance(frames, torch.Tensor) or not frames.is_cuda:
+        raise RuntimeError("frames must be a CUDA tensor: the PCGmix kernels have no CPU path")
+    if frames.dtype != torch.int32:
+        raise TypeError(f"frames must be int32 on the device, got {frames.dtype}")
+    if frames.dim() != 2 or frames.shape[1] < 5:
+        raise ValueError("frames must be (B, >=5)")
+    if frames.shape[0] > 1 and (frames.stride(1) != 1 or frames.stride(0) < 5):
+        raise ValueError("frames rows must be unit-stride with a row stride >= 5")
+    stride = frames.stride(0) if frames.shape[0] > 1 else max(5, frames.stride(0))
+    return frames.data_ptr(), int(stride)
+
+
+def _stream_handle(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def version() -> int:
+    return load().pcgmix_version()
+
+
+def device_info():
+    sm, major, minor = _c_i32(), _c_i32(), _c_i32()
+    _check(load().pcgmix_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)), "pcgmix_device_info")
+    return sm.value, major.value, minor.value
+
+
+def _same_device(*tensors):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError("all tensors must live on the same CUDA device")
+    return dev
+
+
+def mix1d(x, out, frames, mix, lam32, one_minus_lam32, order=None, err_flag=None):
+    """``out[B,C,L] = PCGmix(x)``; see ``pcgmix_mix1d`` in the header."""
+    global launch_count
+    if x.dim() != 3 or out.shape != x.shape:
+        raise ValueError("x and out must be (B, C, L) of equal shape")
+    B, C, L = x.shape
+    dev = _same_device(x, out, frames, mix, order, err_flag)
+    fptr, fstride = _frames_ptr(frames)
+    with torch.cuda.device(dev):
+        rc = load().pcgmix_mix1d(
+            _dev_ptr(x, torch.float32, "x"), _dev_ptr(out, torch.float32, "out"),
+            fptr, fstride, _dev_ptr(mix, torch.int32, "mix"),
+            _dev_ptr(order, torch.int32, "order", True), float(lam32), float(one_minus_lam32), B, C, L,
+            _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+    _check(rc, "pcgmix_mix1d")
+    launch_count += 1 if B > 0 else 0
+
+
+def mix1d_magwarp(x, out, frames, mix, lam32, one_minus_lam32, knots, coefmat, knot_pos, knot,
+                  order=None, err_flag=None):
+    """Fused PCGmix+; see ``pcgmix_mix1d_magwarp`` in the header."""
+    global launch_count
+    if x.dim() != 3 or out.shape != x.shape:
+        raise ValueError("x and out must be (B, C, L) of equal shape")
+    B, C, L = x.shape
+    if tuple(knots.shape) != (B, knot + 2, C):
+        raise ValueError(f"knots must be (B, knot+2, C) = {(B, knot + 2, C)}, got {tuple(knots.shape)}")
+    if tuple(coefmat.shape) != ((knot + 1) * 4, knot + 2) or tuple(knot_pos.shape) != (knot + 2,):
+        raise ValueError("coefmat / knot_pos do not match knot")
+    dev = _same_device(x, out, frames, mix, order, err_flag, knots, coefmat, knot_pos)
+    fptr, fstride = _frames_ptr(frames)
+    with torch.cuda.device(dev):
+        rc = load().pcgmix_mix1d_magwarp(
+            _dev_ptr(x, torch.float32, "x"), _dev_ptr(out, torch.float32, "out"),
+            fptr, fstride, _dev_ptr(mix, torch.int32, "mix"),
+            _dev_ptr(order, torch.int32, "order", True), float(lam32), float(one_minus_lam32),
+            _dev_ptr(knots, torch.float64, "knots"), _dev_ptr(coefmat, torch.float64, "coefmat"),
+            _dev_ptr(knot_pos, torch.float64, "knot_pos"), int(knot), B, C, L,
+            _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+    _check(rc, "pcgmix_mix1d_magwarp")
+    launch_count += 1 if B > 0 else 0
+
+
+def mix2d(x, out, frames, mix, lam32, one_minus_lam32, tbox=None, h1=0, h2=0, order=None, err_flag=None):
+    """PCGmix on (B, Ch, F, T) with the optional zero box; see ``pcgmix_mix2d`` in the header."""
+    global launch_count
+    if x.dim() != 4 or out.shape != x.shape:
+        raise ValueError("x and out must be (B, Ch, F, T) of equal shape")
+    B, Ch, F, T = x.shape
+    dev = _same_device(x, out, frames, mix, order, err_flag, tbox)
+    fptr, fstride = _frames_ptr(frames)
+    with torch.cuda.device(dev):
+        rc = load().pcgmix_mix2d(
+            _dev_ptr(x, torch.float32, "x"), _dev_ptr(out, torch.float32, "out"),
+            fptr, fstride, _dev_ptr(mix, torch.int32, "mix"),
+            _dev_ptr(order, torch.int32, "order", True), float(lam32), float(one_minus_lam32), B, Ch, F, T,
+            _dev_ptr(tbox, torch.int32, "tbox", True), int(h1), int(h2),
+            _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+    _check(rc, "pcgmix_mix2d")
+    launch_count += 1 if B > 0 else 0
+
+
+def segment_dense(states, downsample, cycles, cycle_count, err_flag=None):
+    global launch_count
+    R, T = states.shape
+    dev = _same_device(states, cycles, cycle_count, err_flag)
+    with torch.cuda.device(dev):
+        rc = load().pcgmix_segment_dense(
+            _dev_ptr(states, torch.int8, "states"), R, T, int(downsample),
+            _dev_ptr(cycles, torch.int32, "cycles"), cycles.shape[0], _dev_ptr(cycle_count, torch.int32, "cycle_count"),
+            _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+    _check(rc, "pcgmix_segment_dense")
+    launch_count += 3 if R > 0 else 0
+
+
+def segment_table(positions, codes, rec_offsets, downsample, spec_cols, rec_len, cycles, cycle_count, err_flag=None):
+    global launch_count
+    R = rec_offsets.shape[0] - 1
+    dev = _same_device(positions, codes, rec_offsets, rec_len, cycles, cycle_count, err_flag)
+    with torch.cuda.device(dev):
+        rc = load().pcgmix_segment_table(
+            _dev_ptr(positions, torch.int32, "positions"), _dev_ptr(codes, torch.int8, "codes"),
+            _dev_ptr(rec_offsets, torch.int32, "rec_offsets"), R, int(downsample), int(spec_cols),
+            _dev_ptr(rec_len, torch.int32, "rec_len", True), _dev_ptr(cycles, torch.int32, "cycles"),
+            cycles.shape[0], _dev_ptr(cycle_count, torch.int32, "cycle_count"),
+            _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+    _check(rc, "pcgmix_segment_table")
+    launch_count += 3 if R > 0 else 0
+
+
+def cut_cycles(signal, cycles, n_cycles, out, n_cycles_dev=None):
+    global launch_count
+    R, C, T = signal.shape
+    L = out.shape[-1]
+    dev = _same_device(signal, cycles, out, n_cycles_dev)
+    with torch.cuda.device(dev):
+        rc = load().pcgmix_cut_cycles(
+            _dev_ptr(signal, torch.float32, "signal"), R, C, T, _dev_ptr(cycles, torch.int32, "cycles"),
+            int(n_cycles), _dev_ptr(n_cycles_dev, torch.int32, "n_cycles_dev", True),
+            _dev_ptr(out, torch.float32, "out"), L, _stream_handle(dev))
+    _check(rc, "pcgmix_cut_cycles")
+    launch_count += 1 if n_cycles > 0 else 0
+
+
+def duration_features(frames, n, fs, features, err_flag=None):
+    global launch_count
+    dev = _same_device(frames, features, err_flag)
+    fptr, fstride = _frames_ptr(frames)
+    with torch.cuda.device(dev):
+        rc = load().pcgmix_duration_features(
+            fptr, fstride, int(n), int(fs),
+            _dev_ptr(features, torch.float64, "features"), _dev_ptr(err_flag, torch.int32, "err_flag", True),
+            _stream_handle(dev))
+    _check(rc, "pcgmix_duration_features")
+    launch_count += 1 if n > 0 else 0

@@ -1,0 +1,72 @@
+"""Host -> device upload of the small per-step arrays (frames, pairing, order, knots).
+
+All arrays of one step are packed into ONE pinned host buffer and moved with ONE asynchronous
+copy on the current stream; the device side is one allocation sliced into typed views.  No
+``cudaMalloc`` per call (PyTorch's caching allocator), no host synchronisation except when a
+pinned slot is about to be reused while its previous copy is still in flight (a ring of slots
+makes that rare).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence
+
+import numpy as np
+import torch
+
+_ALIGN = 16
+_RING = 4
+
+
+class _Slot:
+    def __init__(self):
+        self.buf = None
+        self.event = None
+
+
+class Uploader:
+    def __init__(self):
+        self._slots = {}
+        self._next = {}
+
+    def _slot(self, device: torch.device, nbytes: int) -> _Slot:
+        key = (device.type, device.index)
+        ring = self._slots.setdefault(key, [_Slot() for _ in range(_RING)])
+        i = self._next.get(key, 0)
+        self._next[key] = (i + 1) % _RING
+        slot = ring[i]
+        if slot.event is not None:
+            slot.event.synchronize()          # previous copy out of this slot must have finished
+        if slot.buf is None or slot.buf.numel() < nbytes:
+            slot.buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, pin_memory=True)
+        return slot
+
+    def upload(self, arrays: Sequence[np.ndarray], device: torch.device) -> List[torch.Tensor]:
+        """Copy ``arrays`` (C-contiguous ndarrays) to ``device``; returns tensors of the same
+        shapes/dtypes, all views into one device allocation."""
+        offsets, total = [], 0
+        for a in arrays:
+            total = (total + _ALIGN - 1) // _ALIGN * _ALIGN
+            offsets.append(total)
+            total += a.nbytes
+        total = max(total, _ALIGN)
+        slot = self._slot(device, total)
+        host = slot.buf.numpy()
+        for a, off in zip(arrays, offsets):
+            host[off:off + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+        dev_buf = torch.empty(total, dtype=torch.uint8, device=device)
+        dev_buf.copy_(slot.buf[:total], non_blocking=True)
+        if slot.event is None:
+            slot.event = torch.cuda.Event()
+        slot.event.record(torch.cuda.current_stream(device))
+        out = []
+        for a, off in zip(arrays, offsets):
+            t = dev_buf[off:off + a.nbytes].view(torch.from_numpy(np.empty(0, a.dtype)).dtype)
+            out.append(t.view(a.shape))
+        return out
+
+
+_default = Uploader()
+
+
+def upload(arrays: Sequence[np.ndarray], device) -> List[torch.Tensor]:
+    return _default.upload(arrays, torch.device(device))

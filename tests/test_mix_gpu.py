@@ -1,0 +1,274 @@
+"""Parity of the CUDA path (through the public ``augment`` and the C ABI) with the CPU oracle and
+with the fixtures produced by the unmodified reference.
+
+Tolerances (BASELINE.json north_star): pairing / indices bit-exact; PCGmix (mix only) bit-exact
+— the kernel performs the same three separately rounded fp32 operations as the reference;
+PCGmix+ within 1e-5 relative of the reference's float64 spline (measured: ~1e-7, >99.99 %
+of samples bit-equal)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pcgmix_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5
+
+
+class _Args:
+    def __init__(self, method, batch):
+        self.method, self.batch_size, self.sample_rate, self.num_classes = method, batch, 1000, 2
+
+
+class _Step:
+    def __init__(self, count):
+        self.count = count
+
+
+def _rel_err(got, want):
+    denom = np.maximum(np.abs(want), np.finfo(np.float32).tiny)
+    return float(np.max(np.abs(got.astype(np.float64) - want.astype(np.float64)) / denom))
+
+
+def _run_1d(method, step, data, labels, frames, wav=None):
+    from pcgmix_b200 import augmentations
+    dev = torch.device("cuda:0")
+    ohe = torch.nn.functional.one_hot(torch.from_numpy(np.asarray(labels)), int(max(2, labels.max() + 1))).to(dev)
+    d = torch.from_numpy(data).to(dev)
+    out, tgt, mix, cut = augmentations.augment(_Args(method, data.shape[0]), d, ohe, torch.from_numpy(frames),
+                                               wav or ["a0001"] * data.shape[0], _Step(step), None, dev, None)
+    torch.cuda.synchronize()
+    assert cut is None
+    return out, tgt, mix, d
+
+
+GOLDEN_MIX = ["pcgmix_c4_l2500", "pcgmix_alpha2_prob", "pcgmix_mixall"]
+GOLDEN_WARP = ["pcgmixplus_c4_l2500", "pcgmixplus_default_c2_l800", "pcgmixplus_alpha_k2_oddlen",
+               "pcgmixplus_k7_c3", "pcgmixplus_mixall"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_MIX)
+def test_pcgmix_bit_exact_vs_reference_fixture(golden, name):
+    g = golden(name)
+    out, tgt, mix, d_in = _run_1d(str(g["method"]), int(g["step"]), g["data"], g["labels"], g["frames"])
+    assert np.array_equal(mix, g["mix"]) and mix.dtype == np.int64
+    got = out.cpu().numpy()
+    assert out.data_ptr() != d_in.data_ptr() and out.dtype == torch.float32 and out.is_contiguous()
+    assert np.array_equal(got.view(np.uint32), g["out"].view(np.uint32))
+    assert np.array_equal(d_in.cpu().numpy(), g["data"]), "input batch was modified"
+    assert np.array_equal(tgt.cpu().numpy().astype(np.float32), g["target"].astype(np.float32))
+
+
+@pytest.mark.parametrize("name", GOLDEN_WARP)
+def test_pcgmix_plus_vs_reference_fixture(golden, name):
+    g = golden(name)
+    out, tgt, mix, _ = _run_1d(str(g["method"]), int(g["step"]), g["data"], g["labels"], g["frames"])
+    assert np.array_equal(mix, g["mix"])
+    got = out.cpu().numpy()
+    assert _rel_err(got, g["out"]) <= REL_TOL
+    assert np.mean(got == g["out"]) > 0.999, "fp64 spline should reproduce almost every sample bit-for-bit"
+    assert np.array_equal(tgt.cpu().numpy().astype(np.float32), g["target"].astype(np.float32))
+
+
+@pytest.mark.parametrize("tag", ["samepcg", "samedataset"])
+def test_pairing_modifiers(golden, tag):
+    g = golden(f"pcgmix_{tag}")
+    out, _, mix, _ = _run_1d(str(g["method"]), int(g["step"]), g["data"], g["labels"], g["frames"],
+                             wav=[str(w) for w in g["wav"]])
+    assert np.array_equal(mix, g["mix"])
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), g["out"].view(np.uint32))
+
+
+def test_gate_failure_returns_same_objects(golden):
+    from pcgmix_b200 import augmentations
+    g = golden("pcgmix_gate_fail")
+    dev = torch.device("cuda:0")
+    d = torch.from_numpy(g["data"]).to(dev)
+    ohe = torch.nn.functional.one_hot(torch.from_numpy(g["labels"]), 2).to(dev)
+    out, tgt, mix, cut = augmentations.augment(_Args(str(g["method"]), 4), d, ohe, torch.from_numpy(g["frames"]),
+                                               ["a"] * 4, _Step(int(g["step"])), None, dev, None)
+    assert out is d and tgt is ohe and mix == [] and cut is None
+
+
+def test_unknown_method_passthrough():
+    from pcgmix_b200 import augmentations
+    d = torch.zeros(2, 1, 8, device="cuda:0")
+    out, tgt, mix, cut = augmentations.augment(_Args("nothing", 2), d, None, None, None, _Step(0), None, "cuda:0", None)
+    assert out is d and mix == [] and cut is None
+
+
+def test_pairs_edge_cases_through_c_abi(golden):
+    """Every (i, j) pair of the edge-case cycles, one kernel launch: cycle k = (i, j) mixes row i
+    with partner row n*n + j."""
+    from pcgmix_b200 import native
+    g = golden("pairs_1d_edge")
+    x, fr = g["data"], g["frames"]
+    n, c, length = x.shape
+    data = np.concatenate([np.repeat(x, n, axis=0), x], axis=0)                       # (n*n + n, c, L)
+    frames = np.concatenate([np.repeat(fr, n, axis=0), fr], axis=0).astype(np.int32)
+    mix = np.concatenate([n * n + np.tile(np.arange(n), n), np.arange(n * n, n * n + n)]).astype(np.int32)
+    dev = torch.device("cuda:0")
+    d = torch.from_numpy(data).to(dev)
+    out = torch.empty_like(d)
+    lam = np.float32(g["lam"])
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    native.mix1d(d, out, torch.from_numpy(frames).to(dev), torch.from_numpy(mix).to(dev), lam,
+                 np.float32(1) - lam, err_flag=err)
+    got = out.cpu().numpy()[: n * n].reshape(n, n, c, length)
+    assert int(err.item()) == 0
+    assert np.array_equal(got.view(np.uint32), g["out"].view(np.uint32))
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 7), (3, 2, 33), (5, 4, 2500), (9, 3, 1001), (4, 1, 4400), (6, 5, 250)])
+@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)"])
+def test_random_shapes_vs_oracle(shape, method):
+    from pcgmix_b200 import synth
+    b, c, length = shape
+    rng = np.random.default_rng(b * 1000 + length)
+    frames = synth.cycle_frames(rng, b, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    labels = rng.integers(0, 2, b)
+    step = 17
+    out, _, mix, _ = _run_1d(method, step, data, labels, frames)
+    want, want_mix, _, _ = orc.augment_1d(method, data.copy(), labels, frames, step)
+    assert np.array_equal(mix, want_mix)
+    got = out.cpu().numpy()
+    if "magwarp" in method:
+        assert _rel_err(got, want) <= REL_TOL
+    else:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+def test_misaligned_base_pointer_uses_scalar_path():
+    """A batch whose storage does not start on a 16-byte boundary must still be exact."""
+    from pcgmix_b200 import native, synth
+    rng = np.random.default_rng(3)
+    b, c, length = 6, 2, 404
+    frames = synth.cycle_frames(rng, b, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    mix = rng.permutation(b).astype(np.int32)
+    dev = torch.device("cuda:0")
+    backing = torch.zeros(b * c * length + 1, device=dev)
+    d = backing[1:].view(b, c, length)
+    d.copy_(torch.from_numpy(data))
+    assert d.data_ptr() % 16 != 0
+    out = torch.empty(b, c, length, device=dev)
+    lam = np.float32(0.37)
+    native.mix1d(d, out, torch.from_numpy(frames.astype(np.int32)).to(dev), torch.from_numpy(mix).to(dev), lam,
+                 np.float32(1) - lam)
+    want = orc.mix_batch(data, frames, mix, lam)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_lambda_one_and_special_values():
+    """lambda = 1: samples equal x1 wherever the partner is finite; NaN/Inf/-0 propagate like IEEE."""
+    from pcgmix_b200 import native
+    dev = torch.device("cuda:0")
+    x = np.zeros((2, 1, 16), np.float32)
+    x[0, 0, :] = np.arange(16)
+    x[0, 0, 3] = -0.0
+    x[1, 0, :] = 5
+    x[1, 0, 2] = np.inf
+    x[1, 0, 5] = np.nan
+    frames = np.array([[0, 4, 8, 12, 16], [0, 4, 8, 12, 16]], np.int32)
+    mix = np.array([1, 0], np.int32)
+    for lam in (np.float32(1.0), np.float32(0.25)):
+        out = torch.empty(2, 1, 16, device=dev)
+        native.mix1d(torch.from_numpy(x).to(dev), out, torch.from_numpy(frames).to(dev), torch.from_numpy(mix).to(dev),
+                     lam, np.float32(1) - lam)
+        want = orc.mix_batch(x, frames, mix, lam)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+def test_invalid_frames_are_rejected_on_host_and_flagged_on_device():
+    from pcgmix_b200 import augmentations, native
+    dev = torch.device("cuda:0")
+    d = torch.randn(2, 1, 32, device=dev)
+    ohe = torch.nn.functional.one_hot(torch.tensor([0, 0]), 2).to(dev)
+    bad = torch.tensor([[0, 10, 5, 20, 30], [0, 5, 10, 20, 30]])
+    with pytest.raises(ValueError):
+        augmentations.augment(_Args("durratiomixup", 2), d, ohe, bad, ["a"] * 2, _Step(1), None, dev, None)
+    too_long = torch.tensor([[0, 5, 10, 20, 40], [0, 5, 10, 20, 30]])
+    with pytest.raises(ValueError):
+        augmentations.augment(_Args("durratiomixup", 2), d, ohe, too_long, ["a"] * 2, _Step(1), None, dev, None)
+    # device-resident frames cannot be validated on the host: the kernel copies the cycle and flags it
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.empty_like(d)
+    native.mix1d(d, out, bad.to(torch.int32).to(dev), torch.tensor([1, 7], dtype=torch.int32, device=dev),
+                 0.5, 0.5, err_flag=err)
+    torch.cuda.synchronize()
+    assert int(err.item()) == (native.ERR_BAD_FRAMES | native.ERR_BAD_PARTNER)
+    assert torch.equal(out, d)
+
+
+def test_cpu_tensor_is_refused():
+    from pcgmix_b200 import augmentations
+    d = torch.randn(2, 1, 32)
+    ohe = torch.nn.functional.one_hot(torch.tensor([0, 0]), 2)
+    fr = torch.tensor([[0, 5, 10, 20, 30]] * 2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        augmentations.augment(_Args("durratiomixup", 2), d, ohe, fr, ["a"] * 2, _Step(1), None, "cpu", None)
+
+
+def test_order_does_not_change_result():
+    from pcgmix_b200 import draws, native, synth
+    rng = np.random.default_rng(11)
+    b, c, length = 64, 4, 2500
+    frames = synth.cycle_frames(rng, b, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    mix = rng.permutation(b)
+    dev = torch.device("cuda:0")
+    d = torch.from_numpy(data).to(dev)
+    f = torch.from_numpy(frames.astype(np.int32)).to(dev)
+    m = torch.from_numpy(mix.astype(np.int32)).to(dev)
+    o1, o2 = torch.empty_like(d), torch.empty_like(d)
+    native.mix1d(d, o1, f, m, 0.3, 0.7)
+    order = draws.processing_order(mix)
+    assert sorted(order.tolist()) == list(range(b))
+    native.mix1d(d, o2, f, m, 0.3, 0.7, order=torch.from_numpy(order).to(dev))
+    assert torch.equal(o1, o2)
+
+
+def test_large_batch_properties_full_size():
+    """BASELINE config 2 size (B=4096, C=4, L=2500): checked through size-independent properties
+    and a vectorised oracle on a slice."""
+    from pcgmix_b200 import augmentations, synth
+    rng = np.random.default_rng(synth.BENCH_SEED)
+    b, c, length = 4096, 4, 2500
+    frames = synth.cycle_frames(rng, b, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    labels = rng.integers(0, 2, b)
+    out, _, mix, d_in = _run_1d("durratiomixup", 5, data, labels, frames)
+    got = out.cpu().numpy()
+    # pairing is a within-class permutation
+    assert sorted(mix.tolist()) == list(range(b)) and np.array_equal(labels[mix], labels)
+    # samples outside every blended window are copies of the input; padding stays zero
+    lam32 = orc.lambda_as_float32(orc.draw_lambda(1, 5))
+    want = orc.mix_batch_vectorised(data, frames, mix, lam32)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    t = np.arange(length)[None, None, :]
+    assert not got[np.broadcast_to(t >= frames[:, 4][:, None, None], got.shape)].any()
+    # linearity in lambda: out(lam) - x1 == (1-lam) * (x2 - x1) only on blended samples -> checksum of
+    # unblended region equals the input's
+    changed = got != data
+    assert changed.sum() <= c * synth.mixed_samples(frames, mix)
+
+
+def test_pcgmix_plus_large_batch_sampled():
+    from pcgmix_b200 import synth
+    rng = np.random.default_rng(synth.BENCH_SEED + 1)
+    b, c, length = 2048, 4, 2500
+    frames = synth.cycle_frames(rng, b, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    labels = rng.integers(0, 2, b)
+    step = 9
+    out, _, mix, _ = _run_1d("durmixmagwarp(0.2,4)", step, data, labels, frames)
+    got = out.cpu().numpy()
+    lam32 = orc.lambda_as_float32(orc.draw_lambda(1, step))
+    knots = orc.draw_knots(b, 4, c, 0.2)
+    mixed = orc.mix_batch_vectorised(data, frames, mix, lam32)
+    sample = rng.choice(b, 64, replace=False)
+    curves = orc.warp_curves(length, knots[sample])
+    want = (mixed[sample].astype(np.float64) * curves).astype(np.float32)
+    assert _rel_err(got[sample], want) <= REL_TOL
