@@ -37,6 +37,7 @@ struct MixArgs {
     const double* coefmat;     // [(K+1)*4][K+2]
     const double* knot_pos;    // [K+2]
     double inv_h;              // (K+1)/(P-1)
+    uint32_t piece_magic;      // floor(2^32*(K+1)/(P-1)), rounded down: umulhi(t, magic) <= piece(t)
     int32_t K;
     // zero box (2D composites)
     const int32_t* tbox;       // [B][2] or nullptr

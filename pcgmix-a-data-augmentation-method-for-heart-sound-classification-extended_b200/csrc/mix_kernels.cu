@@ -7,19 +7,29 @@
 //   augmentations2d.py:206-221, :419-426 the spectrogram variant; :286-395 the zero boxes
 //
 // One pass over HBM: every output element is produced from one read of the cycle itself
-// (vector loads, streaming), an optional read of the partner's sample (only where the state
-// windows overlap) and one vector store.  Nothing is a contraction, so there is no tensor-core
-// work here; the bound is HBM bandwidth (DESIGN.md section "Roofline").
+// (128-bit streaming loads), an optional read of the partner's sample (only where the state
+// windows overlap) and one 128-bit streaming store.  Nothing is a contraction, so there is no
+// tensor-core work here; the bound is HBM bandwidth ("Roofline").
 //
 // Layout: a cycle is R rows of pitch P floats, contiguous.  The partner sample of (row, t) in
-// state s sits at the SAME row, column t + (f2[s]-f1[s]), i.e. at a constant flat shift per
-// state, so the whole cycle is handled as one flat array of R*P floats and rows only matter
-// for "which column is this" (t = flat mod P).
+// state s sits in the SAME row at column t + (f2[s]-f1[s]), i.e. at a constant flat shift per
+// state.  Two work decompositions share one kernel body:
+//   ROWS  a CTA owns a slice of ONE row (P % VEC == 0): column = slice start + vector index,
+//         no division anywhere; grid = (cycle slot, slice, row)
+//   FLAT  a CTA owns a slice of the cycle's flat R*P array (rows not vector-aligned, e.g.
+//         T = 250 spectrogram columns): (row, column) advance incrementally per vector
+//
+// Instruction budget matters as much as bytes here (at 6.5 TB/s an SM has ~55 issue slots per
+// 128-bit vector per warp... the first version of this kernel spent 290 on it): the per-cycle state
+// table lives in shared memory as four int4 {start, blended length, partner shift, next start},
+// one LDS.128 per vector after three compares; the block size is a template parameter so every
+// global address is "base + immediate".
 //
 // Numerics: the blend is __fadd_rn(__fmul_rn(a,lam), __fmul_rn(b,1-lam)) — three separately
 // rounded fp32 operations like the reference's tensor expression; an FMA here would break
-// bit parity.  The warp factor is evaluated in fp64 and the product
-// fp64(mixed)*w is rounded once to fp32, like the reference's float64 product stored to fp32.
+// bit parity.  The warp factor is a float64 Horner evaluation and the
+// product fp64(mixed)*w is rounded once to fp32, like the reference's float64 product stored
+// into a float32 array.
 
 #include "common.cuh"
 
@@ -28,7 +38,6 @@ namespace pcgmix {
 namespace {
 
 constexpr int kUnroll = 4;          // vectors per thread, all loads issued before first use
-constexpr int kMaxThreads = 256;
 
 template <int VEC> struct Vec;
 template <> struct Vec<4> {
@@ -58,27 +67,18 @@ template <> struct Vec<1> {
     }
 };
 
-// Per-cycle state windows, broadcast into registers of every thread.
-struct Windows {
-    int lo[4];   // start of state s in this cycle
-    int n[4];    // number of blended samples in state s (min of the two durations)
-    int d[4];    // flat shift to the partner's sample: f2[s] - f1[s]
-};
-
-__device__ __forceinline__ int pick4(int s, int a0, int a1, int a2, int a3) {
-    int r = a0;
-    r = (s == 1) ? a1 : r;
-    r = (s == 2) ? a2 : r;
-    r = (s == 3) ? a3 : r;
-    return r;
+// Exact int -> double for 0 <= i < 2^31 without the (slow) I2F.F64 conversion pipe:
+// 2^52 + i is exactly representable; subtracting 2^52 leaves i.
+__device__ __forceinline__ double int_to_double(int i) {
+    return __hiloint2double(0x43300000, i) - 4503599627370496.0;
 }
 
-// Lanes 0..4 of every warp fetch the five offsets of the cycle and of its partner; durations,
-// window lengths and shifts come from warp shuffles.  No shared memory, no block barrier: each
-// warp runs ahead on its own.  Invalid input (partner out of range, offsets not monotone or
-// outside [0,P]) degrades to "copy the cycle" and raises a bit in *err.
-__device__ __forceinline__ Windows load_windows(const MixArgs& a, int b, int& partner, unsigned& bad) {
-    const int lane = threadIdx.x & 31;
+// Warp 0 builds the cycle's state table: lanes 0..4 fetch the five offsets of the cycle and of
+// its partner, durations / blended lengths / shifts come from warp shuffles (the per-cycle
+// prefix sums are already in the offsets).  Invalid input (partner out of range, offsets not
+// monotone or outside [0,P]) degrades to "copy the cycle" and raises a bit in *err.
+__device__ __forceinline__ void build_windows(const MixArgs& a, int b, int4* s_win, int* s_partner, bool report) {
+    const int lane = threadIdx.x;
     int p = __ldg(a.mix + b);
     const bool bad_partner = static_cast<unsigned>(p) >= static_cast<unsigned>(a.B);
     if (bad_partner) p = b;
@@ -95,90 +95,84 @@ __device__ __forceinline__ Windows load_windows(const MixArgs& a, int b, int& pa
     const unsigned bad_frames = __ballot_sync(kFullMask, (lane < 4) && !ok);
     int n = min(len1, len2);
     if (bad_frames != 0u || bad_partner) n = 0;
-    const int shift = f2 - f1;
-    Windows w;
-#pragma unroll
-    for (int s = 0; s < 4; ++s) {
-        w.lo[s] = __shfl_sync(kFullMask, f1, s);
-        w.n[s] = __shfl_sync(kFullMask, n, s);
-        w.d[s] = __shfl_sync(kFullMask, shift, s);
+    // "next start": the column where the state after s begins; P closes the last one
+    const int next = (lane < 3) ? f1n : a.P;
+    if (lane < 4) s_win[lane] = make_int4(f1, n, f2 - f1, next);
+    if (lane == 0) {
+        *s_partner = p;
+        const unsigned bad = (bad_partner ? PCGMIX_ERR_BAD_PARTNER : 0u) | (bad_frames ? PCGMIX_ERR_BAD_FRAMES : 0u);
+        if (bad != 0u && report && a.err != nullptr) atomicOr(a.err, static_cast<int>(bad));
     }
-    partner = p;
-    bad = (bad_partner ? PCGMIX_ERR_BAD_PARTNER : 0u) | (bad_frames ? PCGMIX_ERR_BAD_FRAMES : 0u);
-    return w;
 }
 
-// Which piece of the spline holds integer sample t: the same bracket SciPy's PPoly uses
-// (knot_pos[k] <= t < knot_pos[k+1], last piece closed on the right).
-__device__ __forceinline__ int spline_piece(double td, double inv_h, int K, const double* kpos) {
-    int k = min(static_cast<int>(td * inv_h), K);
-    if (td < kpos[k]) {
-        --k;
-    } else if (k < K && td >= kpos[k + 1]) {
-        ++k;
-    }
-    return max(k, 0);
-}
-
-__device__ __forceinline__ double spline_eval(const double* c, double dt) {
-    // c[0..3] multiply dt^3, dt^2, dt^1, dt^0
-    return fma(fma(fma(c[0], dt, c[1]), dt, c[2]), dt, c[3]);
-}
-
-template <int VEC, bool MAGWARP, bool BOX>
-__global__ void __launch_bounds__(kMaxThreads)
+template <int VEC, int T, bool ROWS, bool MAGWARP, bool BOX>
+__global__ void __launch_bounds__(T, (MAGWARP ? 1024 : 1280) / T)
 mix_kernel(const __grid_constant__ MixArgs a) {
-    __shared__ __align__(16) double s_coef[MAGWARP ? 2 : 1][MAGWARP ? kMaxPieces * 4 : 1];
+    static_assert(!MAGWARP || ROWS, "the fused warp needs row-aligned slices");
+    __shared__ int4 s_win[4];
+    __shared__ int s_partner;
+    __shared__ __align__(16) double s_coef[MAGWARP ? kMaxPieces * 4 : 2];
     __shared__ double s_kpos[MAGWARP ? kMaxPieces + 1 : 1];
+    __shared__ int s_kint[MAGWARP ? kMaxPieces + 1 : 1];
 
-    const int slot = blockIdx.x / a.chunks_per_cycle;
-    const int chunk = blockIdx.x - slot * a.chunks_per_cycle;
+    const int slot = blockIdx.x;
     const int b = a.order ? __ldg(a.order + slot) : slot;
-    const int vbeg = chunk * a.chunk_len;
-    const int vend = min(vbeg + a.chunk_len, a.nvec);
-    const float* __restrict__ xb = a.x + static_cast<size_t>(b) * a.n_per_cycle;
-    float* __restrict__ ob = a.out + static_cast<size_t>(b) * a.n_per_cycle;
+    // first vector of this CTA, in vector units from the start of the cycle, and its column
+    int vbeg, vend, row = 0, col0;
+    if constexpr (ROWS) {
+        row = blockIdx.z;
+        const int seg_beg = blockIdx.y * a.chunk_len;                 // within the row
+        const int seg_end = min(seg_beg + a.chunk_len, a.P / VEC);
+        const int row_base = row * (a.P / VEC);
+        vbeg = row_base + seg_beg;
+        vend = row_base + seg_end;
+        col0 = (seg_beg + threadIdx.x) * VEC;
+    } else {
+        vbeg = blockIdx.y * a.chunk_len;
+        vend = min(vbeg + a.chunk_len, a.nvec);
+        const int e = (vbeg + threadIdx.x) * VEC;
+        row = e / a.P;
+        col0 = e - row * a.P;
+    }
+    const size_t cyc = static_cast<size_t>(b) * a.n_per_cycle;
+    const int v0 = vbeg + threadIdx.x;
+    const float* __restrict__ own_ptr = a.x + cyc + static_cast<size_t>(v0) * VEC;
+    float* __restrict__ out_ptr = a.out + cyc + static_cast<size_t>(v0) * VEC;
+    const int left = vend - v0;                                        // vector k is live iff k*T < left
 
     // 1. The cycle's own samples do not depend on the windows: get them in flight first.
     Vec<VEC> own[kUnroll];
 #pragma unroll
-    for (int k = 0; k < kUnroll; ++k) {
-        const int v = vbeg + threadIdx.x + k * blockDim.x;
-        if (v < vend) own[k] = Vec<VEC>::load_stream(xb + static_cast<size_t>(v) * VEC);
-    }
+    for (int k = 0; k < kUnroll; ++k)
+        if (k * T < left) own[k] = Vec<VEC>::load_stream(own_ptr + k * T * VEC);
 
-    // 2. State windows of this cycle against its partner.
-    int partner;
-    unsigned bad;
-    const Windows w = load_windows(a, b, partner, bad);
-    if (bad != 0u && chunk == 0 && threadIdx.x == 0 && a.err != nullptr) atomicOr(a.err, static_cast<int>(bad));
-    const float* __restrict__ xp = a.x + static_cast<size_t>(partner) * a.n_per_cycle;
-
-    // 3. PCGmix+: cubic coefficients of the (at most two) rows this chunk touches.
-    int row_first = 0;
+    // 2. State table of this cycle against its partner; spline coefficients of this row.
+    if (threadIdx.x < 32) build_windows(a, b, s_win, &s_partner, ROWS ? (blockIdx.y == 0 && blockIdx.z == 0) : blockIdx.y == 0);
     if constexpr (MAGWARP) {
-        row_first = (vbeg * VEC) / a.P;
         const int n_knots = a.K + 2;
         const int n_coef = (a.K + 1) * 4;
-        for (int i = threadIdx.x; i < 2 * n_coef; i += blockDim.x) {
-            const int rr = (i >= n_coef) ? 1 : 0;
-            const int ci = i - rr * n_coef;
-            const int row = row_first + rr;
-            if (row < a.R) {
-                const double* m = a.coefmat + static_cast<size_t>(ci) * n_knots;
-                const double* y = a.knots + static_cast<size_t>(b) * n_knots * a.R + row;
-                double acc = 0.0;
-                for (int j = 0; j < n_knots; ++j) acc = fma(__ldg(m + j), __ldg(y + static_cast<size_t>(j) * a.R), acc);
-                s_coef[rr][ci] = acc;
-            }
+        // the last warps of the CTA build the coefficients while warp 0 chases partner -> offsets
+        for (int i = (T - 1) - threadIdx.x; i < n_coef; i += T) {
+            const double* m = a.coefmat + static_cast<size_t>(i) * n_knots;
+            const double* y = a.knots + static_cast<size_t>(b) * n_knots * a.R + row;
+            double acc = 0.0;
+            for (int j = 0; j < n_knots; ++j) acc = fma(__ldg(m + j), __ldg(y + static_cast<size_t>(j) * a.R), acc);
+            s_coef[i] = acc;
         }
-        for (int i = threadIdx.x; i < n_knots; i += blockDim.x) s_kpos[i] = __ldg(a.knot_pos + i);
-        __syncthreads();
+        for (int i = (T - 33) - static_cast<int>(threadIdx.x); i >= 0 && i < n_knots; i += T) {
+            const double kp = __ldg(a.knot_pos + i);
+            s_kpos[i] = kp;
+            // first integer sample that belongs to the piece starting at this knot; the bracket
+            // kpos[k] <= t < kpos[k+1] of SciPy's PPoly becomes kint[k] <= t < kint[k+1]
+            s_kint[i] = (i == n_knots - 1) ? 0x7fffffff : static_cast<int>(ceil(kp));
+        }
     }
+    __syncthreads();
+    const int lo1 = s_win[1].x, lo2 = s_win[2].x, lo3 = s_win[3].x;
+    const float* __restrict__ par_ptr = a.x + static_cast<size_t>(s_partner) * a.n_per_cycle + static_cast<size_t>(v0) * VEC;
 
     int tb0 = 0, tb1 = 0;
     if constexpr (BOX) {
-        tb0 = 0;
         tb1 = a.P;
         if (a.tbox != nullptr) {
             tb0 = __ldg(a.tbox + static_cast<size_t>(b) * 2);
@@ -186,100 +180,91 @@ mix_kernel(const __grid_constant__ MixArgs a) {
         }
     }
 
-    // 4. (row, column) of this thread's first vector; later vectors advance by a fixed step.
-    int e0 = (vbeg + threadIdx.x) * VEC;
-    int row = e0 / a.P;
-    int t0 = e0 - row * a.P;
-
-    bool mixed[kUnroll][VEC];
+    // 3. Per vector: which state, how many leading samples blend, where the partner's are.
+    int live[kUnroll];          // bit e set: sample e of vector k is blended
     float other[kUnroll][VEC];
-    int rows[kUnroll], cols[kUnroll];
-
+    int cols[kUnroll], rows[kUnroll];
+    int col = col0;
 #pragma unroll
     for (int k = 0; k < kUnroll; ++k) {
-        const int v = vbeg + threadIdx.x + k * blockDim.x;
+        cols[k] = col;
         rows[k] = row;
-        cols[k] = t0;
-        if (v < vend) {
-            const int s0 = (t0 >= w.lo[1]) + (t0 >= w.lo[2]) + (t0 >= w.lo[3]);
-            const int bound = pick4(s0, w.lo[1], w.lo[2], w.lo[3], a.P);
-            int src[VEC];
-            if (t0 + (VEC - 1) < bound) {
-                // whole vector inside one state of one row (the common case)
-                const int lo = pick4(s0, w.lo[0], w.lo[1], w.lo[2], w.lo[3]);
-                const int n = pick4(s0, w.n[0], w.n[1], w.n[2], w.n[3]);
-                const int d = pick4(s0, w.d[0], w.d[1], w.d[2], w.d[3]);
+        live[k] = 0;
+        if (k * T < left) {
+            const int s = (col >= lo1) + (col >= lo2) + (col >= lo3);
+            const int4 w = s_win[s];                                   // {start, blended, shift, next start}
+            const int ahead = col - w.x;
+            if (__builtin_expect(ahead >= 0 && col + (VEC - 1) < w.w, 1)) {
+                // whole vector inside one state of one row: samples e < m blend, partner is contiguous
+                const int m = w.y - ahead;
+                const float* src = par_ptr + k * T * VEC + w.z;
 #pragma unroll
-                for (int e = 0; e < VEC; ++e) {
-                    mixed[k][e] = static_cast<unsigned>(t0 + e - lo) < static_cast<unsigned>(n);
-                    src[e] = e0 + e + d;
-                }
+                for (int e = 0; e < VEC; ++e) other[k][e] = (e < m) ? __ldg(src + e) : 0.0f;
+                live[k] = (1 << min(max(m, 0), VEC)) - 1;
             } else {
-                // vector straddles a state start or a row end: decide per sample
+                // vector straddles a state start or a row end (or precedes f[0] > 0): per sample
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    int t = t0 + e;
-                    if (t >= a.P) t -= a.P;
-                    const int s = (t >= w.lo[1]) + (t >= w.lo[2]) + (t >= w.lo[3]);
-                    const int lo = pick4(s, w.lo[0], w.lo[1], w.lo[2], w.lo[3]);
-                    const int n = pick4(s, w.n[0], w.n[1], w.n[2], w.n[3]);
-                    const int d = pick4(s, w.d[0], w.d[1], w.d[2], w.d[3]);
-                    mixed[k][e] = static_cast<unsigned>(t - lo) < static_cast<unsigned>(n);
-                    src[e] = e0 + e + d;
+                    int t = col + e;
+                    if (!ROWS && t >= a.P) t -= a.P;
+                    const int se = (t >= lo1) + (t >= lo2) + (t >= lo3);
+                    const int4 we = s_win[se];
+                    other[k][e] = 0.0f;
+                    if (static_cast<unsigned>(t - we.x) < static_cast<unsigned>(we.y)) {
+                        other[k][e] = __ldg(par_ptr + k * T * VEC + e + we.z);
+                        live[k] |= 1 << e;
+                    }
                 }
             }
-#pragma unroll
-            for (int e = 0; e < VEC; ++e) other[k][e] = mixed[k][e] ? __ldg(xp + src[e]) : 0.0f;
         }
-        e0 += blockDim.x * VEC;
-        t0 += a.rstep;
-        row += a.qstep;
-        if (t0 >= a.P) {
-            t0 -= a.P;
-            ++row;
+        if constexpr (ROWS) {
+            col += T * VEC;
+        } else {
+            col += a.rstep;
+            row += a.qstep;
+            if (col >= a.P) {
+                col -= a.P;
+                ++row;
+            }
         }
     }
 
-    // 5. Blend, warp, box, store.
+    // 4. Blend, warp, box, store.
 #pragma unroll
     for (int k = 0; k < kUnroll; ++k) {
-        const int v = vbeg + threadIdx.x + k * blockDim.x;
-        if (v >= vend) continue;
-        Vec<VEC> res;
+        if (!(k * T < left)) continue;
+        Vec<VEC> res = own[k];
+        if (live[k] != 0) {                                            // most vectors lie outside every window
 #pragma unroll
-        for (int e = 0; e < VEC; ++e) {
-            const float mine = own[k].v[e];
-            const float blended = __fadd_rn(__fmul_rn(mine, a.lam), __fmul_rn(other[k][e], a.one_minus_lam));
-            res.v[e] = mixed[k][e] ? blended : mine;
+            for (int e = 0; e < VEC; ++e) {
+                const float blended = __fadd_rn(__fmul_rn(res.v[e], a.lam), __fmul_rn(other[k][e], a.one_minus_lam));
+                res.v[e] = (live[k] >> e & 1) ? blended : res.v[e];
+            }
         }
         if constexpr (MAGWARP) {
             const int t = cols[k];
-            const double td = static_cast<double>(t);
-            const int piece = spline_piece(td, a.inv_h, a.K, s_kpos);
-            const bool one_piece = (t + (VEC - 1) < a.P) &&
-                                   (piece == a.K || static_cast<double>(t + (VEC - 1)) < s_kpos[piece + 1]);
-            if (one_piece) {
-                const double* c = &s_coef[rows[k] - row_first][piece * 4];
-                const double c0 = c[0], c1 = c[1], c2 = c[2], c3 = c[3];
-                const double dt = td - s_kpos[piece];
+            // piece from an integer reciprocal guess (never above the true piece), then one fix-up
+            int piece = min(static_cast<int>(__umulhi(static_cast<unsigned>(t), a.piece_magic)), a.K);
+            while (t >= s_kint[piece + 1]) ++piece;                    // at most one step unless rows are tiny
+            if (__builtin_expect(t + (VEC - 1) < s_kint[piece + 1], 1)) {
+                const double2 c01 = *reinterpret_cast<const double2*>(&s_coef[piece * 4]);
+                const double2 c23 = *reinterpret_cast<const double2*>(&s_coef[piece * 4 + 2]);
+                const double dt = int_to_double(t) - s_kpos[piece];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
                     const double de = dt + static_cast<double>(e);
-                    const double wv = fma(fma(fma(c0, de, c1), de, c2), de, c3);
+                    const double wv = fma(fma(fma(c01.x, de, c01.y), de, c23.x), de, c23.y);
                     res.v[e] = static_cast<float>(static_cast<double>(res.v[e]) * wv);
                 }
             } else {
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    int te = t + e;
-                    int re = rows[k];
-                    if (te >= a.P) {
-                        te -= a.P;
-                        ++re;
-                    }
-                    const double ted = static_cast<double>(te);
-                    const int pe = spline_piece(ted, a.inv_h, a.K, s_kpos);
-                    const double wv = spline_eval(&s_coef[re - row_first][pe * 4], ted - s_kpos[pe]);
+                    const int te = t + e;
+                    int pe = min(static_cast<int>(__umulhi(static_cast<unsigned>(te), a.piece_magic)), a.K);
+                    while (te >= s_kint[pe + 1]) ++pe;
+                    const double de = int_to_double(te) - s_kpos[pe];
+                    const double* c = &s_coef[pe * 4];
+                    const double wv = fma(fma(fma(c[0], de, c[1]), de, c[2]), de, c[3]);
                     res.v[e] = static_cast<float>(static_cast<double>(res.v[e]) * wv);
                 }
             }
@@ -289,7 +274,7 @@ mix_kernel(const __grid_constant__ MixArgs a) {
             for (int e = 0; e < VEC; ++e) {
                 int te = cols[k] + e;
                 int re = rows[k];
-                if (te >= a.P) {
+                if (!ROWS && te >= a.P) {
                     te -= a.P;
                     ++re;
                 }
@@ -297,34 +282,55 @@ mix_kernel(const __grid_constant__ MixArgs a) {
                 if (f >= a.h1 && f < a.h2 && te >= tb0 && te < tb1) res.v[e] = 0.0f;
             }
         }
-        res.store_stream(ob + static_cast<size_t>(v) * VEC);
+        res.store_stream(out_ptr + k * T * VEC);
     }
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-template <int VEC>
-cudaError_t launch_vec(MixArgs a, bool magwarp, bool box, cudaStream_t stream) {
-    a.nvec = a.n_per_cycle / VEC;
-    int target = kMaxThreads * kUnroll;                    // vector units per CTA
-    if (magwarp) target = max(1, min(target, a.P / VEC));  // a chunk may touch at most two rows
-    a.chunks_per_cycle = ceil_div(a.nvec, target);
-    a.chunk_len = ceil_div(a.nvec, a.chunks_per_cycle);
-    int threads = ceil_div(ceil_div(a.chunk_len, kUnroll), 32) * 32;
-    threads = max(32, min(threads, kMaxThreads));
-    a.qstep = (threads * VEC) / a.P;
-    a.rstep = (threads * VEC) % a.P;
-    const long long grid = static_cast<long long>(a.B) * a.chunks_per_cycle;
-    if (grid <= 0 || grid > 2147483647LL) return cudaErrorInvalidConfiguration;
-    const dim3 g(static_cast<unsigned>(grid)), t(static_cast<unsigned>(threads));
-    if (magwarp) {
-        mix_kernel<VEC, true, false><<<g, t, 0, stream>>>(a);
-    } else if (box) {
-        mix_kernel<VEC, false, true><<<g, t, 0, stream>>>(a);
+template <int VEC, int T, bool ROWS>
+cudaError_t launch_t(const MixArgs& a, dim3 grid, bool magwarp, bool box, cudaStream_t stream) {
+    if constexpr (ROWS) {
+        if (magwarp) {
+            mix_kernel<VEC, T, true, true, false><<<grid, T, 0, stream>>>(a);
+            return cudaGetLastError();
+        }
+    }
+    if (box) {
+        mix_kernel<VEC, T, ROWS, false, true><<<grid, T, 0, stream>>>(a);
     } else {
-        mix_kernel<VEC, false, false><<<g, t, 0, stream>>>(a);
+        mix_kernel<VEC, T, ROWS, false, false><<<grid, T, 0, stream>>>(a);
     }
     return cudaGetLastError();
+}
+
+// Pick the block size (a template parameter) that wastes the fewest thread slots on a slice of
+// `len` vectors; a slice holds at most T*kUnroll vectors.
+template <int VEC, bool ROWS>
+cudaError_t launch_pick(MixArgs a, int units, bool magwarp, bool box, cudaStream_t stream) {
+    // units = vectors per row (ROWS) or per cycle (FLAT)
+    const int cap = 256 * kUnroll;
+    const int slices = ceil_div(units, cap);
+    a.chunk_len = ceil_div(units, slices);
+    a.chunks_per_cycle = slices;
+    const int need = ceil_div(a.chunk_len, kUnroll);            // threads that have work
+    int T = 256;
+    if (VEC == 4) T = need <= 128 ? 128 : need <= 160 ? 160 : need <= 192 ? 192 : need <= 224 ? 224 : 256;
+    a.qstep = (T * VEC) / a.P;
+    a.rstep = (T * VEC) % a.P;
+    if (a.B > 2147483647 || slices > 65535 || (ROWS && a.R > 65535)) return cudaErrorInvalidConfiguration;
+    const dim3 grid(static_cast<unsigned>(a.B), static_cast<unsigned>(slices), ROWS ? static_cast<unsigned>(a.R) : 1u);
+    if constexpr (VEC == 4) {
+        switch (T) {
+            case 128: return launch_t<4, 128, ROWS>(a, grid, magwarp, box, stream);
+            case 160: return launch_t<4, 160, ROWS>(a, grid, magwarp, box, stream);
+            case 192: return launch_t<4, 192, ROWS>(a, grid, magwarp, box, stream);
+            case 224: return launch_t<4, 224, ROWS>(a, grid, magwarp, box, stream);
+            default: return launch_t<4, 256, ROWS>(a, grid, magwarp, box, stream);
+        }
+    } else {
+        return launch_t<1, 256, ROWS>(a, grid, magwarp, box, stream);
+    }
 }
 
 }  // namespace
@@ -332,10 +338,26 @@ cudaError_t launch_vec(MixArgs a, bool magwarp, bool box, cudaStream_t stream) {
 cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t stream) {
     MixArgs a = base;
     a.n_per_cycle = a.R * a.P;
+    if (magwarp) {
+        // floor(2^32 * (K+1)/(P-1)) rounded down: umulhi(t, magic) never exceeds the true piece
+        const double ratio = static_cast<double>(a.K + 1) / static_cast<double>(a.P - 1);
+        const double scaled = ratio * 4294967296.0 * (1.0 - 1e-9);
+        a.piece_magic = scaled >= 4294967295.0 ? 4294967295u : static_cast<unsigned>(scaled);
+    }
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out)) & 15u) == 0;
-    const bool wide_rows = !magwarp || a.P >= 4;   // a PCGmix+ chunk may span at most two rows
-    if (aligned16 && (a.n_per_cycle % 4) == 0 && wide_rows) return launch_vec<4>(a, magwarp, box, stream);
-    return launch_vec<1>(a, magwarp, box, stream);
+    const bool rows_fit_grid = a.R <= 65535;
+    if (aligned16 && (a.P % 4) == 0 && rows_fit_grid) {
+        a.nvec = a.n_per_cycle / 4;
+        return launch_pick<4, true>(a, a.P / 4, magwarp, box, stream);
+    }
+    if (!magwarp && aligned16 && (a.n_per_cycle % 4) == 0) {
+        a.nvec = a.n_per_cycle / 4;
+        return launch_pick<4, false>(a, a.nvec, magwarp, box, stream);
+    }
+    a.nvec = a.n_per_cycle;
+    if (rows_fit_grid) return launch_pick<1, true>(a, a.P, magwarp, box, stream);
+    if (magwarp) return cudaErrorInvalidConfiguration;
+    return launch_pick<1, false>(a, a.nvec, magwarp, box, stream);
 }
 
 }  // namespace pcgmix
