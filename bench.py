@@ -62,6 +62,14 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-order", action="store_true", help="visit cycles in index order instead of pairing-chain order")
+    ap.add_argument("--kernel", default="pipeline", choices=["pipeline", "direct"],
+                    help="pipeline: persistent TMA-pipelined kernel (default); direct: direct-load kernel")
+    ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--max-slice", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--pbuf-pct", type=int, default=0)
+    ap.add_argument("--consumer-threads", type=int, default=0)
+    ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: 1 no stores, 2 no arithmetic, 4 no partner staging")
     return ap.parse_args()
 
 
@@ -277,6 +285,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     native.load()
+    native.set_tuning(args.kernel == "pipeline", args.stages, args.max_slice, args.ctas_per_sm, args.pbuf_pct,
+                      args.consumer_threads, args.debug_skip)
 
     B, C, L = args.batch, args.channels, args.length
     K, W = args.steps, args.warmup
@@ -412,6 +422,7 @@ def run_b200(args):
                        "l2_policy": f"inputs larger than L2: {NB} x {in_bytes / 1e6:.0f} MB input batches + 2 output "
                                     "buffers rotate, every step reads/writes ~330 MB",
                        "cycle_order": "index" if args.no_order else "pairing-chain",
+                       "kernel": args.kernel, "stages": args.stages, "max_slice": args.max_slice, "ctas_per_sm": args.ctas_per_sm,
                        "sharding": "batches per rank, pairing inside each batch, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,

@@ -67,6 +67,23 @@ const char* pcgmix_last_error(void); /* thread-local, valid until the next faili
 int pcgmix_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
 
 /*
+ * Kernel selection knobs (process-wide; meant for benchmarking, the defaults are the tuned ones).
+ *   use_pipeline  1: rows of >= 1024 floats with P % 4 == 0 and 16-byte-aligned tensors go through
+ *                 the persistent TMA-pipelined kernel; 0: always the direct-load kernel
+ *   stages        shared-memory ring depth of the pipelined kernel (1..8; 0 = default)
+ *   max_slice     elements of a row handled per pipeline step (multiple of 4; 0 = default)
+ *   ctas_per_sm   cap on resident CTAs per SM (0 = as many as fit)
+ *   pbuf_pct      shared-memory budget for staged partner windows, in % of a slice (0 = default);
+ *                 slices whose windows do not fit read the partner straight from global memory
+ *   consumer_threads  lower bound on consumer threads per CTA (0 = just enough for one slice)
+ *   debug         must be 0; non-zero values switch parts of the pipelined kernel off for
+ *                 profiling (1 no stores, 2 no arithmetic, 4 no partner staging) and give wrong output
+ * Results do not depend on any of these.
+ */
+int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, int32_t ctas_per_sm,
+                      int32_t pbuf_pct, int32_t consumer_threads, int32_t debug);
+
+/*
  * PCGmix on time series.
  *   x, out ....... [B][C][L] fp32, contiguous, must not alias
  *   frames ....... int32, row b at frames + b*frame_stride: the five cumulative state offsets

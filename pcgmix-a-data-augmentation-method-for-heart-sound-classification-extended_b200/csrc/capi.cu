@@ -10,6 +10,15 @@ namespace {
 
 thread_local char g_error[512] = "";
 
+pcgmix::PipelineTuning g_tuning = {1, 0, 0, 0, 0, 0, 0};
+
+cudaError_t dispatch_mix(const pcgmix::MixArgs& a, bool magwarp, bool box, cudaStream_t stream) {
+    if (g_tuning.enabled && pcgmix::pipeline_applicable(a, box)) {
+        return pcgmix::launch_mix_pipeline(a, magwarp, g_tuning, stream);
+    }
+    return pcgmix::launch_mix(a, magwarp, box, stream);
+}
+
 int fail(const char* what) {
     std::snprintf(g_error, sizeof(g_error), "%s", what);
     return 1;
@@ -53,6 +62,19 @@ int pcgmix_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) 
     return 0;
 }
 
+int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, int32_t ctas_per_sm, int32_t pbuf_pct,
+                      int32_t consumer_threads, int32_t debug) {
+    if (stages < 0 || stages > 8 || max_slice < 0 || (max_slice % 4) != 0 || ctas_per_sm < 0) return fail("bad tuning value");
+    g_tuning.enabled = use_pipeline ? 1 : 0;
+    g_tuning.stages = stages;
+    g_tuning.max_slice = max_slice;
+    g_tuning.ctas_per_sm = ctas_per_sm;
+    g_tuning.pbuf_pct = pbuf_pct;
+    g_tuning.consumer_threads = consumer_threads;
+    g_tuning.debug = debug;
+    return 0;
+}
+
 int pcgmix_mix1d(const float* x, float* out, const int32_t* frames, int32_t frame_stride, const int32_t* mix,
                  const int32_t* order, float lam, float one_minus_lam, int32_t B, int32_t C, int32_t L,
                  int32_t* err_flag, pcgmix_stream_t stream) {
@@ -61,7 +83,7 @@ int pcgmix_mix1d(const float* x, float* out, const int32_t* frames, int32_t fram
     pcgmix::MixArgs a{};
     a.x = x; a.out = out; a.frames = frames; a.frame_stride = frame_stride; a.mix = mix; a.order = order;
     a.err = err_flag; a.lam = lam; a.one_minus_lam = one_minus_lam; a.B = B; a.R = C; a.P = L; a.F = 1;
-    const cudaError_t e = pcgmix::launch_mix(a, false, false, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = dispatch_mix(a, false, false, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix1d", e);
 }
 
@@ -79,7 +101,7 @@ int pcgmix_mix1d_magwarp(const float* x, float* out, const int32_t* frames, int3
     a.err = err_flag; a.lam = lam; a.one_minus_lam = one_minus_lam; a.B = B; a.R = C; a.P = L; a.F = 1;
     a.knots = knots; a.coefmat = coefmat; a.knot_pos = knot_pos; a.K = K;
     a.inv_h = static_cast<double>(K + 1) / static_cast<double>(L - 1);
-    const cudaError_t e = pcgmix::launch_mix(a, true, false, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = dispatch_mix(a, true, false, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix1d_magwarp", e);
 }
 
@@ -95,7 +117,7 @@ int pcgmix_mix2d(const float* x, float* out, const int32_t* frames, int32_t fram
     a.err = err_flag; a.lam = lam; a.one_minus_lam = one_minus_lam; a.B = B; a.R = Ch * F; a.P = T;
     a.tbox = tbox; a.F = F; a.h1 = h1 < 0 ? 0 : h1; a.h2 = h2 > F ? F : h2;
     const bool box = a.h1 < a.h2;
-    const cudaError_t e = pcgmix::launch_mix(a, false, box, static_cast<cudaStream_t>(stream));
+    const cudaError_t e = dispatch_mix(a, false, box, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix2d", e);
 }
 

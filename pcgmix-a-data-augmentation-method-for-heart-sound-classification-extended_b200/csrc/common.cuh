@@ -46,8 +46,21 @@ struct MixArgs {
     int32_t h2;
 };
 
-// mix_kernels.cu
+// mix_kernels.cu — direct-load kernel (any shape)
 cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t stream);
+
+// mix_pipeline.cu — persistent TMA-pipelined kernel (rows of >= 1024 floats, P % 4 == 0, aligned)
+struct PipelineTuning {
+    int enabled;        // 0: always use the direct-load kernel
+    int stages;         // ring depth (1..4), 0 = default
+    int max_slice;      // elements per slice (multiple of 4), 0 = default
+    int ctas_per_sm;    // cap on resident CTAs per SM, 0 = as many as fit
+    int pbuf_pct;       // shared-memory budget of the packed partner windows, % of a slice, 0 = default
+    int consumer_threads;  // lower bound on consumer threads per CTA, 0 = just enough for a slice
+    int debug;          // profiling only (results become wrong): 1 skip stores, 2 skip arithmetic, 4 skip partner copies
+};
+bool pipeline_applicable(const MixArgs& a, bool box);
+cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const PipelineTuning& tune, cudaStream_t stream);
 
 // segment_kernels.cu
 cudaError_t launch_segment_dense(const int8_t* states, int32_t R, int32_t T, int32_t downsample,

@@ -1,0 +1,550 @@
+// Persistent, TMA-pipelined PCGmix / PCGmix+ kernel for B200 (sm_100a).
+//
+// Same arithmetic as mix_kernels.cu (see there for the reference lines it replaces and for the
+// numerics rules), different data movement.  The direct-load kernel is bound by latency, not by
+// bytes: every CTA first chases order -> partner -> offsets, then waits for its own loads, and
+// only a few CTAs fit on an SM.  Here the HBM traffic is decoupled from the arithmetic:
+//
+//   producer warp   walks the work list (one item = one slice of one row of one cycle), resolves
+//                   the item's state windows, and issues cp.async.bulk (TMA bulk) copies into a
+//                   ring of shared-memory stages: the row slice itself, plus, for each of the
+//                   four heart states, the 16-byte-aligned superset of the partner's window.
+//                   Completion is signalled on the stage's "full" mbarrier (expect_tx/complete_tx).
+//   consumer warps  wait on "full", blend + warp the slice in place in shared memory (128-bit
+//                   shared loads/stores), fence to the async proxy and arrive on the stage's
+//                   "computed" mbarrier.  Consumer warps never wait for one another.
+//   store warp      waits on "computed", hands the slice to cp.async.bulk for the store to global
+//                   memory, waits until that store has finished READING shared memory and releases
+//                   the stage to the producer through the "empty" mbarrier.
+//
+// No register is tied up by a load in flight, so the number of bytes in flight per SM is set by
+// the ring depth (stages x CTAs per SM), not by occupancy.  Work is distributed round-robin
+// (item i -> CTA i mod grid), so CTAs that run together handle neighbouring slots of the
+// processing order and a cycle read as "partner" is still in L2 when it is read as "itself".
+//
+// Shared-memory layout of a stage (slice_cap floats per slice):
+//   xbuf [slice_cap]        the cycle's own samples, overwritten in place with the result
+//   pbuf [slice_cap + 32]   partner windows, packed; window s starts at a 16-byte boundary
+//   meta                    int4 win[4] = {local start, blended length, pbuf shift, local next
+//                           start}, slice geometry, the row's spline coefficients
+//
+// Requirements (checked by the launcher, which otherwise uses the direct-load kernel): P % 4 == 0,
+// 16-byte-aligned tensors, P >= 1024.
+
+#include "common.cuh"
+
+namespace pcgmix {
+
+namespace {
+
+constexpr int kMaxStages = 8;
+constexpr int kVecPerThread = 2;
+constexpr int kHeaderBytes = 1024;
+constexpr int kHelperThreads = 64;     // the two LAST warps of the CTA: store warp, then load producer
+                                       // (the SM's issue arbiter favours high warp ids; a producer in warp 0
+                                       // is starved by consumer warps polling their barriers)
+
+struct StageMeta {
+    int4 win[4];               // {local start, blended length, shift into pbase, local next start}
+    const float* pbase;        // where partner samples are read from: the stage's pbuf, or (window set too
+                               // large for pbuf) the partner's row in global memory
+    long long out_offset;      // element offset of the slice in x / out
+    int nvec;                  // 128-bit vectors in this slice
+    int t_beg;                 // first column of the slice
+    alignas(16) double coef[kMaxPieces * 4];
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+// Blocking wait.  try_wait parks the thread in hardware for up to `suspend_ns` before it has to
+// be re-issued, so waiting warps do not compete with the producer for issue slots.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t suspend_ns = 2000) {
+    uint32_t done = 0;
+    const uint32_t addr = smem_addr(bar);
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(suspend_ns) : "memory");
+    }
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// shared -> global bulk copy; one bulk group per call
+__device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst_gmem), "r"(smem_addr(src_smem)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// block until at most `pending` of this thread's bulk stores are still reading shared memory
+__device__ __forceinline__ void bulk_store_wait_read(int pending) {
+    switch (pending) {
+        case 0: asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.bulk.wait_group.read 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); break;
+    }
+}
+__device__ __forceinline__ void bulk_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ double int_to_double(int i) {
+    return __hiloint2double(0x43300000, i) - 4503599627370496.0;
+}
+
+struct PipeArgs {
+    int n_items;               // B * R * slices_per_row (checked < 2^31 by the launcher)
+    int step_rest;             // gridDim.x / B  } item -> (slot, rest) advances by these per iteration,
+    int step_slot;             // gridDim.x % B  } so the device never divides
+    int slices_per_row;
+    int slice_len;             // elements per slice (multiple of 4); the last slice of a row may be shorter
+    int slice_cap;             // floats reserved for a slice in shared memory (>= slice_len)
+    int pbuf_cap;              // floats reserved for the packed partner windows of a slice
+    int stages;
+    int stage_bytes;
+    int header_bytes;          // barriers, knot tables and (PCGmix+) the coefficient matrix
+    int debug;                 // profiling only: 1 = skip stores, 2 = skip arithmetic, 4 = skip partner copies
+};
+
+template <int NCT, bool MAGWARP>
+__global__ void __launch_bounds__(NCT + kHelperThreads, (NCT <= 192 ? 4 : NCT <= 320 ? 3 : 2))
+mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ PipeArgs pa) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);                  // loads of the stage have landed
+    uint64_t* computed = full + kMaxStages;                               // consumers are done with the stage
+    uint64_t* empty = computed + kMaxStages;                              // the stage's store has left shared memory
+    double* s_kpos = reinterpret_cast<double*>(smem + 256);               // kMaxPieces+1 doubles (256 B)
+    int* s_kint = reinterpret_cast<int*>(smem + 256 + 256);               // kMaxPieces+1 ints (128 B)
+    double* s_mat = reinterpret_cast<double*>(smem + kHeaderBytes);      // [(K+1)*4][K+2] coefficient matrix
+    unsigned char* stages = smem + pa.header_bytes;
+    const int S = pa.stages;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&computed[s], NCT);
+            mbar_init(&empty[s], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if constexpr (MAGWARP) {
+        const int n_knots = a.K + 2;
+        for (int i = threadIdx.x; i < n_knots; i += NCT + kHelperThreads) {
+            const double kp = __ldg(a.knot_pos + i);
+            s_kpos[i] = kp;
+            s_kint[i] = (i == n_knots - 1) ? 0x7fffffff : static_cast<int>(ceil(kp));
+        }
+        // The matrix must sit in shared memory: with ~216 KB of the SM carved out for the stage
+        // rings, L1 is a few KB and a per-item walk over the matrix in global memory costs a chain
+        // of L2 round trips in the producer (measured: 1.3 us per item, the whole kernel's bound).
+        for (int i = threadIdx.x; i < (a.K + 1) * 4 * n_knots; i += NCT + kHelperThreads) s_mat[i] = __ldg(a.coefmat + i);
+    }
+    __syncthreads();
+
+    auto stage_x = [&](int s) { return reinterpret_cast<float*>(stages + static_cast<size_t>(s) * pa.stage_bytes); };
+    auto stage_p = [&](int s) { return stage_x(s) + pa.slice_cap; };
+    auto stage_meta = [&](int s) { return reinterpret_cast<StageMeta*>(stage_p(s) + pa.pbuf_cap); };
+    // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int n_it = (pa.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+
+    if (threadIdx.x >= NCT + 32) {
+        // ===================================== producer warp =====================================
+        const int lane = threadIdx.x - (NCT + 32);
+        // order[slot] -> mix[b] -> frames[partner] (+ the row's knots) is a chain of dependent loads.
+        // It is software-pipelined across items: cycle ids are fetched three items ahead, partner
+        // ids two, offsets and knots one, so none of their latency sits in front of the copies.
+        struct Cursor { int slot, rest; };                  // item = rest * B + slot
+        auto advance = [&](Cursor c) {
+            c.slot += pa.step_slot;
+            c.rest += pa.step_rest;
+            if (c.slot >= a.B) {
+                c.slot -= a.B;
+                ++c.rest;
+            }
+            return c;
+        };
+        auto cycle_of = [&](Cursor c) { return a.order ? __ldg(a.order + c.slot) : c.slot; };
+        auto row_of = [&](Cursor c) { return pa.slices_per_row == 1 ? c.rest : c.rest / pa.slices_per_row; };
+        auto knot_of = [&](int b, int row) {                // lane j holds knot j of (cycle b, row)
+            double y = 0.0;
+            if constexpr (MAGWARP) {
+                if (lane < a.K + 2 && !(pa.debug & 16)) y = __ldg(a.knots + (static_cast<size_t>(b) * (a.K + 2) + lane) * a.R + row);
+            }
+            return y;
+        };
+        // knots are read exactly once from HBM: pull them into L2 two items ahead so that the real
+        // load (one item ahead) is an L2 hit and fits inside one producer iteration
+        auto warm_knots = [&](int b, int row) {
+            if constexpr (MAGWARP) {
+                if (lane < a.K + 2) {
+                    const double* ptr = a.knots + (static_cast<size_t>(b) * (a.K + 2) + lane) * a.R + row;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+                }
+            }
+        };
+        int b0 = 0, b1 = 0, b2 = 0, p0 = 0, p1 = 0, f1 = 0, f2 = 0;
+        double y0 = 0.0;
+        bool bad0 = false;
+        Cursor c0{static_cast<int>(blockIdx.x % a.B), static_cast<int>(blockIdx.x / a.B)};   // item it
+        Cursor c1 = advance(c0), c2 = advance(c1), c3 = advance(c2);                          // it+1 .. it+3
+        if (n_it > 0) {
+            b0 = cycle_of(c0);
+            p0 = __ldg(a.mix + b0);
+            bad0 = static_cast<unsigned>(p0) >= static_cast<unsigned>(a.B);
+            if (bad0) p0 = b0;
+            if (lane < 5) {
+                f1 = __ldg(a.frames + static_cast<size_t>(b0) * a.frame_stride + lane);
+                f2 = __ldg(a.frames + static_cast<size_t>(p0) * a.frame_stride + lane);
+            }
+            y0 = knot_of(b0, row_of(c0));
+        }
+        if (n_it > 1) {
+            b1 = cycle_of(c1);
+            p1 = __ldg(a.mix + b1);
+            warm_knots(b1, row_of(c1));
+        }
+        if (n_it > 2) b2 = cycle_of(c2);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < n_it; ++it) {
+            const int rest = c0.rest;
+            const int row = row_of(c0);
+            const int slice = rest - row * pa.slices_per_row;
+            const int b = b0;
+            const int p = p0;
+            const bool bad_partner = bad0;
+            const int f1_cur = f1, f2_cur = f2;
+            const double y_cur = y0;
+            // prefetch for the items behind this one
+            bool bad1 = false;
+            if (it + 1 < n_it) {
+                bad1 = static_cast<unsigned>(p1) >= static_cast<unsigned>(a.B);
+                if (bad1) p1 = b1;
+                if (lane < 5) {
+                    f1 = __ldg(a.frames + static_cast<size_t>(b1) * a.frame_stride + lane);
+                    f2 = __ldg(a.frames + static_cast<size_t>(p1) * a.frame_stride + lane);
+                }
+                y0 = knot_of(b1, row_of(c1));
+            }
+            int p2 = 0, b3 = 0;
+            if (it + 2 < n_it) {
+                p2 = __ldg(a.mix + b2);
+                warm_knots(b2, row_of(c2));
+            }
+            if (it + 3 < n_it) b3 = cycle_of(c3);
+            b0 = b1; p0 = p1; bad0 = bad1;
+            b1 = b2; p1 = p2;
+            b2 = b3;
+            c0 = c1; c1 = c2; c2 = c3; c3 = advance(c3);
+
+            double acc[(kMaxPieces * 4 + 31) / 32];
+            if constexpr (MAGWARP) {
+                // coefficient i = sum_j M[i][j] * knot_j; knot_j comes from lane j by shuffle
+                const int n_knots = a.K + 2;
+                const int n_coef = (a.K + 1) * 4;
+#pragma unroll
+                for (int q = 0; q < (kMaxPieces * 4 + 31) / 32; ++q) acc[q] = 0.0;
+#pragma unroll 2
+                for (int j = 0; j < ((pa.debug & 8) ? 0 : n_knots); ++j) {
+                    const double yj = __shfl_sync(kFullMask, y_cur, j);
+#pragma unroll
+                    for (int q = 0; q < (kMaxPieces * 4 + 31) / 32; ++q) {
+                        const int i = lane + q * 32;
+                        if (i < n_coef) acc[q] = fma(s_mat[i * n_knots + j], yj, acc[q]);
+                    }
+                }
+            }
+            const int f1n = __shfl_down_sync(kFullMask, f1_cur, 1);
+            const int f2n = __shfl_down_sync(kFullMask, f2_cur, 1);
+            const int len1 = f1n - f1_cur;
+            const int len2 = f2n - f2_cur;
+            const bool ok = (f1_cur >= 0) & (f2_cur >= 0) & (len1 >= 0) & (len2 >= 0) & (f1n <= a.P) & (f2n <= a.P);
+            const unsigned bad_frames = __ballot_sync(kFullMask, (lane < 4) && !ok);
+            int n = min(len1, len2);
+            if (bad_frames != 0u || bad_partner) n = 0;
+            const int d = f2_cur - f1_cur;
+            const int t_beg = slice * pa.slice_len;
+            const int t_end = min(t_beg + pa.slice_len, a.P);
+            // the part of state `lane`'s blended window that falls into this slice, as a
+            // 16-byte-aligned range [src_lo, src_hi) of the partner's row
+            const int w_beg = max(f1_cur, t_beg);
+            const int w_end = min(f1_cur + n, t_end);
+            bool have = (lane < 4) && (w_end > w_beg);
+            const int src_lo = (w_beg + d) & ~3;
+            const int src_hi = (w_end + d + 3) & ~3;
+            const int cnt = have ? (src_hi - src_lo) : 0;
+            int incl = cnt;
+#pragma unroll
+            for (int s = 1; s < 4; s <<= 1) {
+                const int up = __shfl_up_sync(kFullMask, incl, s);
+                if (lane >= s) incl += up;
+            }
+            const int off = incl - cnt;
+            int total = __shfl_sync(kFullMask, incl, 3);
+            const bool staged = total <= pa.pbuf_cap && !(pa.debug & 4);   // else: consumers read the partner from global memory
+            if (!staged) {
+                have = false;
+                total = 0;
+            }
+
+            // the stage's previous slice (item it-S) must have left shared memory
+            mbar_wait(&empty[stage], phase ^ 1);
+
+            float* xbuf = stage_x(stage);
+            float* pbuf = stage_p(stage);
+            StageMeta* meta = stage_meta(stage);
+            const long long row_off = (static_cast<long long>(b) * a.R + row) * a.P;
+            const long long prow = (static_cast<long long>(p) * a.R + row) * a.P;
+            if (lane < 4) {
+                const int next = (lane < 3) ? f1n : a.P;
+                const int shift = staged ? (t_beg + d - src_lo + off) : d;
+                meta->win[lane] = make_int4(f1_cur - t_beg, n, shift, next - t_beg);
+            }
+            if (lane == 0) {
+                meta->pbase = staged ? pbuf : (a.x + prow + t_beg);
+                meta->out_offset = row_off + t_beg;
+                meta->nvec = (t_end - t_beg) >> 2;
+                meta->t_beg = t_beg;
+                const unsigned bad = (bad_partner ? PCGMIX_ERR_BAD_PARTNER : 0u) | (bad_frames ? PCGMIX_ERR_BAD_FRAMES : 0u);
+                if (bad != 0u && rest == 0 && a.err != nullptr) atomicOr(a.err, static_cast<int>(bad));
+            }
+            if constexpr (MAGWARP) {
+                const int n_coef = (a.K + 1) * 4;
+#pragma unroll
+                for (int q = 0; q < (kMaxPieces * 4 + 31) / 32; ++q)
+                    if (lane + q * 32 < n_coef) meta->coef[lane + q * 32] = acc[q];
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>((t_end - t_beg) + total) * 4u);
+                bulk_load(xbuf, a.x + row_off + t_beg, static_cast<uint32_t>(t_end - t_beg) * 4u, &full[stage]);
+            }
+            if (have) bulk_load(pbuf + off, a.x + prow + src_lo, static_cast<uint32_t>(cnt) * 4u, &full[stage]);
+            if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    } else if (threadIdx.x >= NCT) {
+        // ======================================= store warp ======================================
+        if (threadIdx.x == NCT) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < n_it; ++it) {
+                mbar_wait(&computed[stage], phase);
+                const StageMeta* m = stage_meta(stage);
+                if (!(pa.debug & 1)) bulk_store(a.out + m->out_offset, stage_x(stage), static_cast<uint32_t>(m->nvec) * 16u);
+                bulk_store_wait_read(0);                   // the engine has read the slice out of shared memory
+                mbar_arrive(&empty[stage]);
+                if (++stage == S) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+            bulk_store_wait_all();                         // every result is in global memory before exit
+        }
+    } else {
+        // ===================================== consumer warps ====================================
+        const int ct = threadIdx.x;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < n_it; ++it) {
+            float* xbuf = stage_x(stage);
+            const StageMeta* meta = stage_meta(stage);
+            mbar_wait(&full[stage], phase);
+
+            const int lo1 = meta->win[1].x, lo2 = meta->win[2].x, lo3 = meta->win[3].x;
+            const int nvec = meta->nvec;
+            const int t_beg = meta->t_beg;
+            const float* pbase = meta->pbase;
+#pragma unroll
+            for (int k = 0; k < kVecPerThread; ++k) {
+                const int v = ct + k * NCT;
+                if (v < nvec && !(pa.debug & 2)) {
+                    const int col = v * 4;                                   // local column
+                    const float4 mine = *reinterpret_cast<const float4*>(xbuf + col);
+                    float r[4] = {mine.x, mine.y, mine.z, mine.w};
+                    const int s = (col >= lo1) + (col >= lo2) + (col >= lo3);
+                    const int4 w = meta->win[s];
+                    const int ahead = col - w.x;
+                    if (__builtin_expect(ahead >= 0 && col + 3 < w.w, 1)) {
+                        const int m = w.y - ahead;                           // leading samples that blend
+                        if (m > 0) {
+                            const float* src = pbase + col + w.z;
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                if (e < m) r[e] = __fadd_rn(__fmul_rn(r[e], a.lam), __fmul_rn(src[e], a.one_minus_lam));
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int t = col + e;
+                            const int se = (t >= lo1) + (t >= lo2) + (t >= lo3);
+                            const int4 we = meta->win[se];
+                            if (static_cast<unsigned>(t - we.x) < static_cast<unsigned>(we.y))
+                                r[e] = __fadd_rn(__fmul_rn(r[e], a.lam), __fmul_rn(pbase[t + we.z], a.one_minus_lam));
+                        }
+                    }
+                    if constexpr (MAGWARP) {
+                        const int t = t_beg + col;
+                        int piece = min(static_cast<int>(__umulhi(static_cast<unsigned>(t), a.piece_magic)), a.K);
+                        while (t >= s_kint[piece + 1]) ++piece;
+                        if (__builtin_expect(t + 3 < s_kint[piece + 1], 1)) {
+                            const double2 c01 = *reinterpret_cast<const double2*>(&meta->coef[piece * 4]);
+                            const double2 c23 = *reinterpret_cast<const double2*>(&meta->coef[piece * 4 + 2]);
+                            const double dt = int_to_double(t) - s_kpos[piece];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const double de = dt + static_cast<double>(e);
+                                const double wv = fma(fma(fma(c01.x, de, c01.y), de, c23.x), de, c23.y);
+                                r[e] = static_cast<float>(static_cast<double>(r[e]) * wv);
+                            }
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int te = t + e;
+                                int pe = min(static_cast<int>(__umulhi(static_cast<unsigned>(te), a.piece_magic)), a.K);
+                                while (te >= s_kint[pe + 1]) ++pe;
+                                const double de = int_to_double(te) - s_kpos[pe];
+                                const double* c = &meta->coef[pe * 4];
+                                const double wv = fma(fma(fma(c[0], de, c[1]), de, c[2]), de, c[3]);
+                                r[e] = static_cast<float>(static_cast<double>(r[e]) * wv);
+                            }
+                        }
+                    }
+                    *reinterpret_cast<float4*>(xbuf + col) = make_float4(r[0], r[1], r[2], r[3]);
+                }
+            }
+            fence_async_proxy();                           // my shared-memory writes -> visible to the TMA engine
+            mbar_arrive(&computed[stage]);
+            if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    }
+}
+
+template <int NCT>
+cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, int grid, size_t smem, bool magwarp, cudaStream_t stream) {
+    // opt in to the large dynamic shared-memory carve-out once per kernel instance
+    static bool allowed[2] = {false, false};
+    if (!allowed[magwarp ? 1 : 0]) {
+        const cudaError_t e = magwarp
+            ? cudaFuncSetAttribute(mix_pipeline_kernel<NCT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+            : cudaFuncSetAttribute(mix_pipeline_kernel<NCT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        allowed[magwarp ? 1 : 0] = true;
+    }
+    if (magwarp) {
+        mix_pipeline_kernel<NCT, true><<<grid, NCT + kHelperThreads, smem, stream>>>(a, pa);
+    } else {
+        mix_pipeline_kernel<NCT, false><<<grid, NCT + kHelperThreads, smem, stream>>>(a, pa);
+    }
+    return cudaGetLastError();
+}
+
+int g_sm_count = 0;
+
+}  // namespace
+
+bool pipeline_applicable(const MixArgs& a, bool box) {
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out)) & 15u) == 0;
+    return !box && aligned16 && (a.P % 4) == 0 && a.P >= 1024;
+}
+
+cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const PipelineTuning& tune, cudaStream_t stream) {
+    MixArgs a = base;
+    a.n_per_cycle = a.R * a.P;
+    if (magwarp) {
+        const double ratio = static_cast<double>(a.K + 1) / static_cast<double>(a.P - 1);
+        const double scaled = ratio * 4294967296.0 * (1.0 - 1e-9);
+        a.piece_magic = scaled >= 4294967295.0 ? 4294967295u : static_cast<unsigned>(scaled);
+    }
+    if (g_sm_count == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    PipeArgs pa{};
+    const int max_slice = tune.max_slice > 0 ? (tune.max_slice > 3584 ? 3584 : tune.max_slice) : 3584;   // 448 threads x 2 vectors
+    pa.slices_per_row = (a.P + max_slice - 1) / max_slice;
+    int slice_len = (a.P + pa.slices_per_row - 1) / pa.slices_per_row;
+    slice_len = (slice_len + 3) & ~3;
+    pa.slice_len = slice_len;
+    pa.slice_cap = (slice_len + 31) & ~31;
+    // packed partner windows: physiological cycles blend < 2/3 of a padded row; anything larger
+    // falls back to reading the partner from global memory (still exact, just not staged)
+    const int pbuf_pct = tune.pbuf_pct > 0 ? tune.pbuf_pct : 62;
+    pa.pbuf_cap = ((slice_len * pbuf_pct / 100 + 32) + 31) & ~31;
+    pa.stages = tune.stages > 0 ? (tune.stages > kMaxStages ? kMaxStages : tune.stages) : 4;
+    const size_t stage_bytes = (static_cast<size_t>(pa.slice_cap) + pa.pbuf_cap) * sizeof(float) + sizeof(StageMeta);
+    pa.stage_bytes = static_cast<int>((stage_bytes + 127) & ~static_cast<size_t>(127));
+    const size_t mat_bytes = magwarp ? static_cast<size_t>(a.K + 1) * 4 * (a.K + 2) * sizeof(double) : 0;
+    pa.header_bytes = static_cast<int>((kHeaderBytes + mat_bytes + 127) & ~static_cast<size_t>(127));
+    const size_t smem = pa.header_bytes + static_cast<size_t>(pa.stages) * pa.stage_bytes;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    const long long n_items = static_cast<long long>(a.B) * a.R * pa.slices_per_row;
+    if (n_items > 2147483647LL) return cudaErrorInvalidConfiguration;
+    pa.n_items = static_cast<int>(n_items);
+    pa.debug = tune.debug;
+    const int need = ((slice_len / 4) + kVecPerThread - 1) / kVecPerThread;   // consumer threads with work
+    if (need > 448) return cudaErrorInvalidConfiguration;
+    int nct = need <= 128 ? 128 : need <= 192 ? 192 : need <= 256 ? 256 : need <= 320 ? 320 : need <= 384 ? 384 : 448;
+    if (tune.consumer_threads > nct) {                                   // more (lighter) consumer threads per slice
+        const int want = tune.consumer_threads;
+        nct = want <= 192 ? 192 : want <= 256 ? 256 : want <= 320 ? 320 : want <= 384 ? 384 : 448;
+    }
+    int per_sm = static_cast<int>((228 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : per_sm;
+    const int by_threads = 2048 / (nct + kHelperThreads);
+    per_sm = per_sm < by_threads ? per_sm : by_threads;
+    if (tune.ctas_per_sm > 0 && tune.ctas_per_sm < per_sm) per_sm = tune.ctas_per_sm;
+    long long grid = static_cast<long long>(g_sm_count) * per_sm;
+    if (grid > pa.n_items) grid = pa.n_items;
+    pa.step_rest = static_cast<int>(grid / a.B);
+    pa.step_slot = static_cast<int>(grid % a.B);
+    switch (nct) {
+        case 128: return launch_nct<128>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 192: return launch_nct<192>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 256: return launch_nct<256>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 320: return launch_nct<320>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 384: return launch_nct<384>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        default: return launch_nct<448>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+    }
+}
+
+}  // namespace pcgmix

@@ -34,6 +34,7 @@ SIGNATURES = {
     "pcgmix_version": [],
     "pcgmix_last_error": [],
     "pcgmix_device_info": [_ptr, _ptr, _ptr],
+    "pcgmix_set_tuning": [_c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32],
     "pcgmix_mix1d": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _c_i32, _c_i32, _c_i32, _ptr, _ptr],
     "pcgmix_mix1d_magwarp": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _ptr, _ptr, _ptr,
                              _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr],
@@ -130,6 +131,14 @@ def device_info():
     sm, major, minor = _c_i32(), _c_i32(), _c_i32()
     _check(load().pcgmix_device_info(ctypes.byref(sm), ctypes.byref(major), ctypes.byref(minor)), "pcgmix_device_info")
     return sm.value, major.value, minor.value
+
+
+def set_tuning(use_pipeline: bool = True, stages: int = 0, max_slice: int = 0, ctas_per_sm: int = 0,
+               pbuf_pct: int = 0, consumer_threads: int = 0, debug: int = 0):
+    """Kernel selection knobs (see ``pcgmix_set_tuning`` in the header); results never depend on them."""
+    _check(load().pcgmix_set_tuning(int(bool(use_pipeline)), int(stages), int(max_slice), int(ctas_per_sm),
+                                    int(pbuf_pct), int(consumer_threads), int(debug)),
+           "pcgmix_set_tuning")
 
 
 def _same_device(*tensors):

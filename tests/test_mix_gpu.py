@@ -13,6 +13,16 @@ from oracle import pcgmix_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["pipeline", "direct"])
+def kernel_choice(request):
+    """Every parity test runs twice: through the persistent TMA-pipelined kernel (used for rows of
+    >= 1024 samples) and with it switched off, i.e. through the direct-load kernel only."""
+    from pcgmix_b200 import native
+    native.set_tuning(use_pipeline=request.param == "pipeline")
+    yield request.param
+    native.set_tuning(use_pipeline=True)
+
 REL_TOL = 1e-5
 
 
@@ -138,6 +148,46 @@ def test_random_shapes_vs_oracle(shape, method):
         assert _rel_err(got, want) <= REL_TOL
     else:
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)"])
+def test_windows_larger_than_the_staging_buffer(method):
+    """Cycles that blend (almost) the whole row: the pipelined kernel cannot stage the partner
+    windows in shared memory and must fall back to reading them from global memory."""
+    rng = np.random.default_rng(77)
+    b, c, length = 12, 2, 2400
+    frames = np.tile(np.array([[0, 600, 1200, 1800, 2400]]), (b, 1))
+    frames[1] = [0, 599, 1201, 1795, 2399]
+    frames[5] = [0, 10, 20, 30, 2400]
+    data = rng.standard_normal((b, c, length)).astype(np.float32)
+    labels = np.zeros(b, dtype=np.int64)
+    out, _, mix, _ = _run_1d(method, 21, data, labels, frames)
+    want, want_mix, _, _ = orc.augment_1d(method, data.copy(), labels, frames, 21)
+    assert np.array_equal(mix, want_mix)
+    got = out.cpu().numpy()
+    if "magwarp" in method:
+        assert _rel_err(got, want) <= REL_TOL
+    else:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("length", [4096, 6000, 10000])
+def test_long_rows_are_sliced(length):
+    """Rows longer than one pipeline slice (e.g. BASELINE config 1's 5 s @ 2 kHz = 10 000 samples)."""
+    from pcgmix_b200 import synth
+    rng = np.random.default_rng(length)
+    b, c = 5, 2
+    frames = synth.cycle_frames(rng, b, fs=2000 if length > 4096 else 1000, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    labels = rng.integers(0, 2, b)
+    for method in ("durratiomixup", "durmixmagwarp(0.2,4)"):
+        out, _, mix, _ = _run_1d(method, 3, data, labels, frames)
+        want, _, _, _ = orc.augment_1d(method, data.copy(), labels, frames, 3)
+        got = out.cpu().numpy()
+        if "magwarp" in method:
+            assert _rel_err(got, want) <= REL_TOL
+        else:
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
 def test_misaligned_base_pointer_uses_scalar_path():
