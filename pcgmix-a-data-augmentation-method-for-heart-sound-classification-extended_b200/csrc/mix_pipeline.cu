@@ -40,7 +40,9 @@ namespace {
 constexpr int kMaxStages = 8;
 constexpr int kVecPerThread = 2;
 constexpr int kHeaderBytes = 1024;
-constexpr int kHelperThreads = 64;     // the two LAST warps of the CTA: store warp, then load producer
+constexpr int kProducerWarps = 2;       // producer warps take alternate items (one warp's instruction stream per
+                                        // item, ~600 dependent instructions with the spline set-up, was the bound)
+constexpr int kHelperThreads = 32 + 32 * kProducerWarps;   // the LAST warps of the CTA: store warp, then producers
                                        // (the SM's issue arbiter favours high warp ids; a producer in warp 0
                                        // is starved by consumer warps polling their barriers)
 
@@ -124,8 +126,10 @@ __device__ __forceinline__ double int_to_double(int i) {
 
 struct PipeArgs {
     int n_items;               // B * R * slices_per_row (checked < 2^31 by the launcher)
-    int step_rest;             // gridDim.x / B  } item -> (slot, rest) advances by these per iteration,
+    int step_rest;             // gridDim.x / B  } item -> (slot, rest) advances by these per item,
     int step_slot;             // gridDim.x % B  } so the device never divides
+    int stepn_rest;            // the same for kProducerWarps items at once
+    int stepn_slot;
     int slices_per_row;
     int slice_len;             // elements per slice (multiple of 4); the last slice of a row may be shorter
     int slice_cap;             // floats reserved for a slice in shared memory (>= slice_len)
@@ -179,14 +183,24 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
 
     if (threadIdx.x >= NCT + 32) {
         // ===================================== producer warp =====================================
-        const int lane = threadIdx.x - (NCT + 32);
+        const int lane = threadIdx.x & 31;
+        const int pw = (threadIdx.x - (NCT + 32)) >> 5;      // this warp handles items pw, pw + kProducerWarps, ...
         // order[slot] -> mix[b] -> frames[partner] (+ the row's knots) is a chain of dependent loads.
         // It is software-pipelined across items: cycle ids are fetched three items ahead, partner
         // ids two, offsets and knots one, so none of their latency sits in front of the copies.
         struct Cursor { int slot, rest; };                  // item = rest * B + slot
-        auto advance = [&](Cursor c) {
+        auto advance1 = [&](Cursor c) {
             c.slot += pa.step_slot;
             c.rest += pa.step_rest;
+            if (c.slot >= a.B) {
+                c.slot -= a.B;
+                ++c.rest;
+            }
+            return c;
+        };
+        auto advance = [&](Cursor c) {                      // to this warp's next item
+            c.slot += pa.stepn_slot;
+            c.rest += pa.stepn_rest;
             if (c.slot >= a.B) {
                 c.slot -= a.B;
                 ++c.rest;
@@ -215,9 +229,11 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         int b0 = 0, b1 = 0, b2 = 0, p0 = 0, p1 = 0, f1 = 0, f2 = 0;
         double y0 = 0.0;
         bool bad0 = false;
+        constexpr int NP = kProducerWarps;
         Cursor c0{static_cast<int>(blockIdx.x % a.B), static_cast<int>(blockIdx.x / a.B)};   // item it
-        Cursor c1 = advance(c0), c2 = advance(c1), c3 = advance(c2);                          // it+1 .. it+3
-        if (n_it > 0) {
+        for (int k = 0; k < pw; ++k) c0 = advance1(c0);
+        Cursor c1 = advance(c0), c2 = advance(c1), c3 = advance(c2);                          // this warp's next three
+        if (n_it > pw) {
             b0 = cycle_of(c0);
             p0 = __ldg(a.mix + b0);
             bad0 = static_cast<unsigned>(p0) >= static_cast<unsigned>(a.B);
@@ -228,15 +244,15 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
             y0 = knot_of(b0, row_of(c0));
         }
-        if (n_it > 1) {
+        if (n_it > pw + NP) {
             b1 = cycle_of(c1);
             p1 = __ldg(a.mix + b1);
             warm_knots(b1, row_of(c1));
         }
-        if (n_it > 2) b2 = cycle_of(c2);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int it = 0; it < n_it; ++it) {
+        if (n_it > pw + 2 * NP) b2 = cycle_of(c2);
+        int stage = pw % S;
+        uint32_t phase = (pw / S) & 1;
+        for (int it = pw; it < n_it; it += NP) {
             const int rest = c0.rest;
             const int row = row_of(c0);
             const int slice = rest - row * pa.slices_per_row;
@@ -247,7 +263,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             const double y_cur = y0;
             // prefetch for the items behind this one
             bool bad1 = false;
-            if (it + 1 < n_it) {
+            if (it + NP < n_it) {
                 bad1 = static_cast<unsigned>(p1) >= static_cast<unsigned>(a.B);
                 if (bad1) p1 = b1;
                 if (lane < 5) {
@@ -257,30 +273,31 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 y0 = knot_of(b1, row_of(c1));
             }
             int p2 = 0, b3 = 0;
-            if (it + 2 < n_it) {
+            if (it + 2 * NP < n_it) {
                 p2 = __ldg(a.mix + b2);
                 warm_knots(b2, row_of(c2));
             }
-            if (it + 3 < n_it) b3 = cycle_of(c3);
+            if (it + 3 * NP < n_it) b3 = cycle_of(c3);
             b0 = b1; p0 = p1; bad0 = bad1;
             b1 = b2; p1 = p2;
             b2 = b3;
             c0 = c1; c1 = c2; c2 = c3; c3 = advance(c3);
 
-            double acc[(kMaxPieces * 4 + 31) / 32];
+            // coefficient i = sum_j M[i][j] * knot_j; knot_j comes from lane j by shuffle.  Lane l owns
+            // coefficients l, l+32, l+64, l+96; all but the first exist only for knot > 7.
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
             if constexpr (MAGWARP) {
-                // coefficient i = sum_j M[i][j] * knot_j; knot_j comes from lane j by shuffle
                 const int n_knots = a.K + 2;
                 const int n_coef = (a.K + 1) * 4;
-#pragma unroll
-                for (int q = 0; q < (kMaxPieces * 4 + 31) / 32; ++q) acc[q] = 0.0;
-#pragma unroll 2
+                const bool wide = n_coef > 32;
+                const double* mrow = s_mat + lane * n_knots;
                 for (int j = 0; j < ((pa.debug & 8) ? 0 : n_knots); ++j) {
                     const double yj = __shfl_sync(kFullMask, y_cur, j);
-#pragma unroll
-                    for (int q = 0; q < (kMaxPieces * 4 + 31) / 32; ++q) {
-                        const int i = lane + q * 32;
-                        if (i < n_coef) acc[q] = fma(s_mat[i * n_knots + j], yj, acc[q]);
+                    if (lane < n_coef) acc0 = fma(mrow[j], yj, acc0);
+                    if (wide) {
+                        if (lane + 32 < n_coef) acc1 = fma(mrow[32 * n_knots + j], yj, acc1);
+                        if (lane + 64 < n_coef) acc2 = fma(mrow[64 * n_knots + j], yj, acc2);
+                        if (lane + 96 < n_coef) acc3 = fma(mrow[96 * n_knots + j], yj, acc3);
                     }
                 }
             }
@@ -340,9 +357,10 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
             if constexpr (MAGWARP) {
                 const int n_coef = (a.K + 1) * 4;
-#pragma unroll
-                for (int q = 0; q < (kMaxPieces * 4 + 31) / 32; ++q)
-                    if (lane + q * 32 < n_coef) meta->coef[lane + q * 32] = acc[q];
+                if (lane < n_coef) meta->coef[lane] = acc0;
+                if (lane + 32 < n_coef) meta->coef[lane + 32] = acc1;
+                if (lane + 64 < n_coef) meta->coef[lane + 64] = acc2;
+                if (lane + 96 < n_coef) meta->coef[lane + 96] = acc3;
             }
             __syncwarp();
             if (lane == 0) {
@@ -350,8 +368,9 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 bulk_load(xbuf, a.x + row_off + t_beg, static_cast<uint32_t>(t_end - t_beg) * 4u, &full[stage]);
             }
             if (have) bulk_load(pbuf + off, a.x + prow + src_lo, static_cast<uint32_t>(cnt) * 4u, &full[stage]);
-            if (++stage == S) {
-                stage = 0;
+            stage += NP;                                   // NP <= S is guaranteed by the launcher
+            if (stage >= S) {
+                stage -= S;
                 phase ^= 1;
             }
         }
@@ -511,6 +530,7 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     const int pbuf_pct = tune.pbuf_pct > 0 ? tune.pbuf_pct : 62;
     pa.pbuf_cap = ((slice_len * pbuf_pct / 100 + 32) + 31) & ~31;
     pa.stages = tune.stages > 0 ? (tune.stages > kMaxStages ? kMaxStages : tune.stages) : 4;
+    if (pa.stages < kProducerWarps) pa.stages = kProducerWarps;
     const size_t stage_bytes = (static_cast<size_t>(pa.slice_cap) + pa.pbuf_cap) * sizeof(float) + sizeof(StageMeta);
     pa.stage_bytes = static_cast<int>((stage_bytes + 127) & ~static_cast<size_t>(127));
     const size_t mat_bytes = magwarp ? static_cast<size_t>(a.K + 1) * 4 * (a.K + 2) * sizeof(double) : 0;
@@ -537,6 +557,9 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     if (grid > pa.n_items) grid = pa.n_items;
     pa.step_rest = static_cast<int>(grid / a.B);
     pa.step_slot = static_cast<int>(grid % a.B);
+    pa.stepn_rest = static_cast<int>((grid * kProducerWarps) / a.B);
+    pa.stepn_slot = static_cast<int>((grid * kProducerWarps) % a.B);
+    if (pa.stages < kProducerWarps) return cudaErrorInvalidConfiguration;
     switch (nct) {
         case 128: return launch_nct<128>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
         case 192: return launch_nct<192>(a, pa, static_cast<int>(grid), smem, magwarp, stream);

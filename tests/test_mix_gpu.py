@@ -131,10 +131,12 @@ def test_pairs_edge_cases_through_c_abi(golden):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 7), (3, 2, 33), (5, 4, 2500), (9, 3, 1001), (4, 1, 4400), (6, 5, 250)])
-@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)"])
+@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)", "durmixmagwarp(0.1,12)", "durmixmagwarp(0.3,0)"])
 def test_random_shapes_vs_oracle(shape, method):
     from pcgmix_b200 import synth
     b, c, length = shape
+    if "magwarp" in method and length < 16 and "12" in method:
+        pytest.skip("more knots than samples: SciPy itself rejects duplicate abscissae")
     rng = np.random.default_rng(b * 1000 + length)
     frames = synth.cycle_frames(rng, b, limit=length)
     data = synth.cycle_signals(rng, frames, (c,), length)
