@@ -123,7 +123,7 @@ int pcgmix_mix2d(const float* x, float* out, const int32_t* frames, int32_t fram
 
 int pcgmix_segment_dense(const int8_t* states, int32_t R, int32_t T, int32_t downsample, int32_t* cycles,
                          int32_t max_cycles, int32_t* cycle_count, int32_t* err_flag, pcgmix_stream_t stream) {
-    if (cycle_count == nullptr || (R > 0 && states == nullptr)) return fail("null pointer argument");
+    if (cycle_count == nullptr || (R > 0 && T > 0 && states == nullptr)) return fail("null pointer argument");
     if (R < 0 || T < 0 || downsample < 1 || max_cycles < 0) return fail("bad size argument");
     if (max_cycles > 0 && cycles == nullptr) return fail("null cycles with max_cycles > 0");
     if ((reinterpret_cast<uintptr_t>(cycles) & 15u) != 0) return fail("cycles must be 16-byte aligned");

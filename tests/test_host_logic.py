@@ -1,0 +1,173 @@
+"""CPU-only checks of the host side: method-string mini-language, seeded draws, spline map,
+processing order, sharding, ABI of the shared library (symbols only — no compute without a GPU)."""
+import ctypes
+import os
+import random
+import re
+
+import numpy as np
+import pytest
+
+from oracle import pcgmix_oracle as orc
+from pcgmix_b200 import build_native, draws, native, sharding, spline, synth
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_parse_1d_methods():
+    p = draws.parse_method_1d("durratiomixup")
+    assert (p.branch, p.probability, p.alpha, p.mix_all) == ("durratiomixup", 1.0, 1.0, False)
+    p = draws.parse_method_1d("(alpha=0.5)durmixmagwarp(0.3,2)+0.9")
+    assert (p.branch, p.probability, p.alpha, p.sigma, p.knot) == ("durmixmagwarp", 0.9, 0.5, 0.3, 2)
+    p = draws.parse_method_1d("durmixmagwarp")
+    assert (p.sigma, p.knot) == (0.2, 4)
+    assert draws.parse_method_1d("(mixAll)durratiomixup").mix_all
+    assert draws.parse_method_1d("no-such-method") is None
+    # reference dispatcher order: these never reach the PCGmix branches -> refuse loudly
+    for method in ("respiratoryscale(12,20)durratiomixup", "timemask+durratiomixup", "cutmix", "mixup(same)"):
+        with pytest.raises(NotImplementedError):
+            draws.parse_method_1d(method)
+    for method in ("(rand)durratiomixup", "(sameCVD)durratiomixup", "(saloptenv)durratiomixup", "(closestknn=3)durmixmagwarp(0.2,4)"):
+        with pytest.raises(NotImplementedError):
+            draws.parse_method_1d(method)
+
+
+def test_parse_2d_methods():
+    assert draws.parse_method_2d("durratiomixup+0.5").probability == 0.5
+    p = draws.parse_method_2d("durmixcutout(0.3,0.9)")
+    assert (p.branch, p.time_region_max, p.freq_region_max) == ("durmixcutout", 0.3, 0.9)
+    assert draws.parse_method_2d("durmixtimemask(7)").time_region_max == 1
+    assert draws.parse_method_2d("durmixfreqmask").freq_region_max == 0.2
+    assert draws.parse_method_2d("durmixmagwarp(0.2,4)") is None       # not a 2D method: passthrough like the reference
+    with pytest.raises(NotImplementedError):
+        draws.parse_method_2d("freqmask")
+
+
+def test_draws_match_oracle_and_known_answers(golden):
+    g = golden("kat_draws")
+    assert draws.gate(7) == g["uniform7"]
+    assert draws.draw_lambda(1, 7) == g["lambda_alpha1_seed7"]
+    assert np.array_equal(draws.draw_knots(2, 4, 4, 0.2), g["normals7"])
+    assert np.array_equal(draws.same_label_pairing(g["labels"], 5), g["same_label_mix_seed5"])
+    rng = np.random.default_rng(0)
+    labels = rng.integers(0, 3, 200)
+    wav = [f"{'abc'[i % 3]}{i % 7:04d}" for i in range(200)]
+    for method in ("durratiomixup", "(samePCG)durratiomixup", "(sameDataset)durratiomixup", "(mixAll)durratiomixup"):
+        assert np.array_equal(draws.pairing(method, labels, wav, 11), orc.pick_pairing(method, labels, wav, 11))
+    lam32, oml = draws.lambda_pair_fp32(0.3)
+    assert lam32.dtype == np.float32 and oml == np.float32(1) - np.float32(0.3)
+    assert draws.mask_geometry(9, 0.4) == orc.mask_draws(9, 0.4)
+
+
+def test_global_numpy_stream_is_left_like_the_reference_leaves_it():
+    draws.draw_lambda(1, 42)
+    a = np.random.normal(size=3)
+    orc.draw_lambda(1, 42)
+    assert np.array_equal(a, np.random.normal(size=3))
+
+
+@pytest.mark.parametrize("length,knot", [(2500, 4), (4400, 4), (1001, 2), (250, 1), (128, 0), (1203, 7), (2500, 30), (17, 4)])
+def test_spline_map_matches_scipy(length, knot):
+    from scipy.interpolate import CubicSpline
+    rng = np.random.default_rng(length + knot)
+    y = rng.normal(1, 0.2, (4, knot + 2))
+    x = np.linspace(0, length - 1.0, knot + 2)
+    ref = np.stack([CubicSpline(x, row)(np.arange(length)) for row in y])
+    got = spline.evaluate(y, length)
+    assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-13
+    pos, mat = spline.magwarp_tables(length, knot)
+    assert np.array_equal(pos, x) and mat.shape == ((knot + 1) * 4, knot + 2)
+
+
+def test_processing_order_is_a_permutation_following_chains():
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 17, 4096):
+        mix = rng.permutation(n)
+        order = draws.processing_order(mix)
+        assert sorted(order.tolist()) == list(range(n))
+        nxt = {int(order[i]): int(order[i + 1]) for i in range(n - 1)}
+        follows = sum(1 for b, c in nxt.items() if mix[b] == c)
+        n_cycles = len({frozenset(_orbit(mix, s)) for s in range(n)}) if n <= 17 else None
+        if n_cycles is not None:
+            assert follows == n - n_cycles          # every step follows the pairing except at chain ends
+
+
+def _orbit(mix, s):
+    seen, b = [], s
+    while b not in seen:
+        seen.append(b)
+        b = int(mix[b])
+    return seen
+
+
+def test_sharding_partitions_batches():
+    n_batches = 245
+    for world in (1, 2, 4, 8):
+        seen = []
+        for rank in range(world):
+            mine = sharding.batches_for_rank(n_batches, rank, world)
+            seen += list(mine)
+            assert all(sharding.step_seed(k) == k for k in mine)
+        assert sorted(seen) == list(range(n_batches))
+    lo, hi = sharding.rows_for_rank(10, 3, 4)
+    assert (lo, hi) == (8, 10) and sharding.rows_for_rank(10, 0, 4) == (0, 3)
+
+
+def test_synthetic_generator_shapes():
+    rng = np.random.default_rng(0)
+    fr = synth.cycle_frames(rng, 50, 1000, 2500)
+    assert fr.shape == (50, 5) and (np.diff(fr, axis=1) >= 0).all() and fr[:, 4].max() <= 2500
+    x = synth.cycle_signals(rng, fr, (4,), 2500)
+    assert x.dtype == np.float32 and not x[np.arange(2500)[None, None, :] >= fr[:, 4][:, None, None] + 0 * x.astype(int)].any()
+    st = synth.dense_states(rng, 3, 10000, 2000)
+    assert st.dtype == np.int8 and set(np.unique(st)) <= {1, 2, 3, 4}
+    sf = synth.spectrogram_frames(rng, 20, 250)
+    assert sf.max() <= 250 and (np.diff(sf, axis=1) >= 0).all()
+
+
+def test_library_exports_every_symbol_in_the_header():
+    """The C ABI in include/pcgmix_b200.h and the built library / ctypes table must agree."""
+    header = open(os.path.join(ROOT, "include", "pcgmix_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char\*)\s+(pcgmix_\w+)\s*\(", header, flags=re.M))
+    assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
+    if not os.path.exists(build_native.LIB_PATH):
+        pytest.skip("library not built yet (run __graft_entry__.build())")
+    lib = ctypes.CDLL(build_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pcgmix_version() >= 100
+    # argument counts of the ctypes table follow the header
+    for name, args in native.SIGNATURES.items():
+        m = re.search(r"^(?:int|const char\*)\s+" + name + r"\s*\(([^;]*?)\)\s*;", header, flags=re.S | re.M)
+        assert m, name
+        params = [p for p in m.group(1).replace("\n", " ").split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), (name, len(params), len(args))
+
+
+def test_no_cpu_fallback_and_loud_failure_without_library(monkeypatch):
+    import torch
+    from pcgmix_b200 import augmentations
+
+    class A:
+        method = "durratiomixup"
+        batch_size = 2
+
+    class S:
+        count = 0
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        augmentations.augment(A(), torch.zeros(2, 1, 8), torch.eye(2, dtype=torch.int64), torch.zeros(2, 5, dtype=torch.int64),
+                              ["a", "b"], S(), None, "cpu", None)
+    monkeypatch.setattr(native, "_lib", None)
+    monkeypatch.setattr(build_native, "LIB_PATH", "/nonexistent/libpcgmix_b200.so")
+    with pytest.raises(native.NativeLibraryError, match="no CPU fallback"):
+        native.load()
+
+
+def test_product_code_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "pcgmix-a-data-augmentation-method-for-heart-sound-classification-extended_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
