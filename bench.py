@@ -176,7 +176,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -215,6 +215,25 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "samples": 0}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def recorded_traffic(default_workload: bool):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/),
+    only for the workload that capture was taken on; otherwise None."""
+    if not default_workload:
+        return None, None
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    try:
+        for name in sorted(os.listdir(pdir)):
+            if name.endswith("_traffic.json"):
+                with open(os.path.join(pdir, name)) as f:
+                    best = (json.load(f), name)
+    except Exception:
+        return None, None
+    if best is None:
+        return None, None
+    return float(best[0]["dram_traffic_bytes_per_launch"]), f"profiles/{best[1]}"
 
 
 def measured_peak():
@@ -361,6 +380,8 @@ def run_b200(args):
     mean_launch_s = statistics.fmean(per_launch_ms) * 1e-3
     achieved = statistics.fmean(bytes_per_launch) / mean_launch_s / 1e9
     peak, peak_src = measured_peak()
+    is_default = (B, C, L, args.method) == (4096, 4, 2500, METHOD) and args.kernel == "pipeline"
+    traffic, traffic_src = recorded_traffic(is_default)
 
     # ---- end to end through the public augment() with host buffers ------------------------------
     E = max(3, min(args.e2e_steps, K))
@@ -425,7 +446,7 @@ def run_b200(args):
                        "kernel": args.kernel, "stages": args.stages, "max_slice": args.max_slice, "ctas_per_sm": args.ctas_per_sm,
                        "sharding": "batches per rank, pairing inside each batch, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": statistics.fmean(bytes_per_launch),
                          "kernel_ms_mean": statistics.fmean(per_launch_ms), "kernel_ms_median": statistics.median(per_launch_ms),
                          "kernel_ms_min": min(per_launch_ms)},
