@@ -34,8 +34,7 @@ def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RE
     mix_indices = draws.same_label_pairing(labels, step)
     lam32, one_minus = draws.lambda_pair_fp32(draws.draw_lambda(1, step))
 
-    uploads = [host_frames(frames, batch, n_time), mix_indices.astype(np.int32),
-               draws.processing_order(mix_indices)]
+    uploads = [host_frames(frames, batch, n_time), mix_indices.astype(np.int32)]
     h1 = h2 = 0
     has_tbox = False
     if plan.branch in ("durmixtimemask", "durmixcutout"):
@@ -53,5 +52,5 @@ def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RE
     on_dev = staging.upload(uploads, data.device)
     data_new = torch.empty_like(data)
     native.mix2d(data, data_new, on_dev[0], on_dev[1], lam32, one_minus,
-                 tbox=on_dev[3] if has_tbox else None, h1=h1, h2=h2, order=on_dev[2])
+                 tbox=on_dev[2] if has_tbox else None, h1=h1, h2=h2)
     return data_new, target_ohe, mix_indices, None
