@@ -1,0 +1,177 @@
+#!/usr/bin/env python
+"""Device-side timing of every BASELINE.json configuration (bench.py covers only the headline
+config 2 in the driver's contract).  One process, one GPU; prints one JSON line per config.
+
+    python benchmarks/run_configs.py [--reps 200]
+
+cfg1  32 recordings x 5 s @ 2 kHz, dense Springer states -> segmentation kernels -> cut + pad to
+      4400 -> durratiomixup (tiny: reported as latency per call, not as a roofline fraction)
+cfg2  durmixmagwarp(0.2,4) on 4096 x 4 x 2500 (the bench.py workload), plus PCGmix on the same batch
+cfg3  2D durratiomixup on 1024 x 1 x 64 x 250
+cfg4  1 M cycles = 245 batches of 4096, seed = batch index (single GPU here; shards by batch)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+
+from pcgmix_b200 import augmentations, draws, native, segmentation, spline, staging, synth  # noqa: E402
+
+PEAK = 6544.7
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timed(fn, reps, warm=10):
+    for _ in range(warm):
+        fn(0)
+    torch.cuda.synchronize()
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+    marks[0].record()
+    for i in range(reps):
+        fn(i)
+        marks[i + 1].record()
+    torch.cuda.synchronize()
+    per = [marks[i].elapsed_time(marks[i + 1]) for i in range(reps)]
+    return statistics.fmean(per), min(per)
+
+
+def emit(name, cycles, ms_mean, ms_min, bytes_per_call=None, **extra):
+    line = {"config": name, "cycles_per_call": cycles, "ms_mean": ms_mean, "ms_min": ms_min,
+            "cycles_per_s": cycles / (ms_mean * 1e-3)}
+    if bytes_per_call is not None:
+        gbs = bytes_per_call / (ms_mean * 1e-3) / 1e9
+        line.update({"algorithmic_bytes": bytes_per_call, "achieved_GBps": gbs, "frac_of_measured_peak": gbs / PEAK})
+    line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def prepared_steps(frames, labels, batch, channels, n_steps, magwarp, dev, nb):
+    steps = []
+    for s in range(n_steps):
+        f, lab = frames[s % nb], labels[s % nb]
+        mix = draws.same_label_pairing(lab, s)
+        lam = draws.lambda_pair_fp32(draws.draw_lambda(1, s))
+        arrays = [f.astype(np.int32), mix.astype(np.int32), draws.processing_order(mix)]
+        if magwarp:
+            arrays.append(draws.draw_knots(batch, 4, channels, 0.2))
+        steps.append((staging.upload(arrays, dev), lam, synth.mixed_samples(f, mix)))
+    return steps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=200)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    native.load()
+    rng = np.random.default_rng(synth.BENCH_SEED)
+
+    # ---------------- cfg1 ----------------
+    n_rec, n_samp, bands, L1 = 32, 10000, 4, 4400
+    states = torch.from_numpy(synth.dense_states(rng, n_rec, n_samp, 2000)).to(dev)
+    signal = torch.from_numpy(rng.standard_normal((n_rec, bands, n_samp)).astype(np.float32)).to(dev)
+    table = segmentation.cycles_from_dense_states(states).check()
+    n_cyc = table.total()
+    cycles = segmentation.cut_cycles(signal, table, L1, n_cyc)
+    labels1 = rng.integers(0, 2, n_cyc)
+    mix1 = torch.from_numpy(draws.same_label_pairing(labels1, 0).astype(np.int32)).to(dev)
+    out1 = torch.empty_like(cycles)
+    ms, mn = timed(lambda i: segmentation.cycles_from_dense_states(states), 50)
+    emit("cfg1/segment_dense (32 x 10000 int8 -> cycle table, 3 launches)", n_cyc, ms, mn)
+    ms, mn = timed(lambda i: segmentation.cut_cycles(signal, table, L1, n_cyc), 50)
+    emit("cfg1/cut_cycles (-> %d x 4 x 4400)" % n_cyc, n_cyc, ms, mn)
+    ms, mn = timed(lambda i: native.mix1d(cycles, out1, table.frames[:n_cyc], mix1, 0.3, 0.7), args.reps)
+    emit("cfg1/durratiomixup (%d cycles x 4 x 4400, frames = cycle table view)" % n_cyc, n_cyc, ms, mn,
+         note="latency-bound: %.1f MB per call" % (2 * cycles.numel() * 4 / 1e6))
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        native.mix1d(cycles, out1, table.frames[:n_cyc], mix1, 0.3, 0.7)
+        with torch.cuda.graph(graph, stream=side):
+            native.mix1d(cycles, out1, table.frames[:n_cyc], mix1, 0.3, 0.7)
+    torch.cuda.synchronize()
+    ms, mn = timed(lambda i: graph.replay(), args.reps)
+    emit("cfg1/durratiomixup replayed from a CUDA graph", n_cyc, ms, mn)
+
+    # ---------------- cfg2 / cfg4 ----------------
+    B, C, L, NB = 4096, 4, 2500, 4
+    frames, labels, data = [], [], []
+    for i in range(NB):
+        r = np.random.default_rng(synth.BENCH_SEED + i)
+        f = synth.cycle_frames(r, B, limit=L)
+        frames.append(f)
+        data.append(torch.from_numpy(synth.cycle_signals(r, f, (C,), L)).to(dev))
+        labels.append(r.integers(0, 2, B))
+    outs = [torch.empty_like(data[0]) for _ in range(2)]
+    for magwarp, name in ((True, "cfg2/durmixmagwarp(0.2,4) 4096 x 4 x 2500"), (False, "cfg2b/durratiomixup 4096 x 4 x 2500")):
+        n_steps = args.reps + 10
+        steps = prepared_steps(frames, labels, B, C, n_steps, magwarp, dev, NB)
+
+        def run(i, steps=steps, magwarp=magwarp):
+            up, lam, _ = steps[i % len(steps)]
+            augmentations.pcgmix_on_device(data[i % NB], up[0], up[1], lam[0], lam[1], up[3] if magwarp else None, 4,
+                                           order_dev=up[2], out=outs[i % 2])
+        ms, mn = timed(run, args.reps)
+        m_mean = statistics.fmean(s[2] for s in steps)
+        emit(name, B, ms, mn, 4.0 * C * (2.0 * L * B + m_mean))
+    n_b = 245
+    steps = prepared_steps(frames, labels, B, C, n_b, True, dev, NB)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(n_b):
+        up, lam, _ = steps[k]
+        augmentations.pcgmix_on_device(data[k % NB], up[0], up[1], lam[0], lam[1], up[3], 4, order_dev=up[2], out=outs[k % 2])
+    e1.record()
+    torch.cuda.synchronize()
+    tot = e0.elapsed_time(e1)
+    emit("cfg4/1M cycles = 245 batches of 4096, PCGmix+, 1 GPU", n_b * B, tot, tot,
+         4.0 * C * (2.0 * L * B * n_b + sum(s[2] for s in steps)))
+
+    # ---------------- cfg3 ----------------
+    B3, F3, T3 = 1024, 64, 250
+    frames3 = synth.spectrogram_frames(rng, B3, T3)
+    data3 = torch.from_numpy(synth.cycle_signals(rng, frames3, (1, F3), T3)).to(dev)
+    out3 = torch.empty_like(data3)
+    labels3 = rng.integers(0, 2, B3)
+    mix3 = draws.same_label_pairing(labels3, 0)
+    up3 = staging.upload([frames3.astype(np.int32), mix3.astype(np.int32), draws.processing_order(mix3)], dev)
+    m3 = synth.mixed_samples(frames3, mix3)
+    ms, mn = timed(lambda i: native.mix2d(data3, out3, up3[0], up3[1], 0.3, 0.7, order=up3[2]), args.reps)
+    emit("cfg3/2D durratiomixup 1024 x 1 x 64 x 250 (65.5 MB in)", B3, ms, mn, 4.0 * F3 * (2.0 * T3 * B3 + m3),
+         note="working set 131 MB ~ L2 size: partly L2-resident across repetitions")
+    B3b = 8192
+    frames3b = synth.spectrogram_frames(rng, B3b, T3)
+    data3b = torch.from_numpy(synth.cycle_signals(rng, frames3b, (1, F3), T3)).to(dev)
+    out3b = torch.empty_like(data3b)
+    mix3b = draws.same_label_pairing(rng.integers(0, 2, B3b), 0)
+    up3b = staging.upload([frames3b.astype(np.int32), mix3b.astype(np.int32), draws.processing_order(mix3b)], dev)
+    ms, mn = timed(lambda i: native.mix2d(data3b, out3b, up3b[0], up3b[1], 0.3, 0.7, order=up3b[2]), 50)
+    emit("cfg3x8/2D durratiomixup 8192 x 1 x 64 x 250 (524 MB in, >> L2)", B3b, ms, mn,
+         4.0 * F3 * (2.0 * T3 * B3b + synth.mixed_samples(frames3b, mix3b)))
+    # reference's real spectrogram shape
+    B5, F5, T5 = 4096, 128, 128
+    frames5 = synth.spectrogram_frames(rng, B5, T5, seconds=2.2)
+    data5 = torch.from_numpy(synth.cycle_signals(rng, frames5, (1, F5), T5)).to(dev)
+    out5 = torch.empty_like(data5)
+    mix5 = draws.same_label_pairing(rng.integers(0, 2, B5), 0)
+    up5 = staging.upload([frames5.astype(np.int32), mix5.astype(np.int32), draws.processing_order(mix5)], dev)
+    ms, mn = timed(lambda i: native.mix2d(data5, out5, up5[0], up5[1], 0.3, 0.7, order=up5[2]), 50)
+    emit("spec128/2D durratiomixup 4096 x 1 x 128 x 128 (268 MB in)", B5, ms, mn,
+         4.0 * F5 * (2.0 * T5 * B5 + synth.mixed_samples(frames5, mix5)))
+
+
+if __name__ == "__main__":
+    main()

@@ -346,16 +346,21 @@ cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t
     }
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out)) & 15u) == 0;
     const bool rows_fit_grid = a.R <= 65535;
-    if (aligned16 && (a.P % 4) == 0 && rows_fit_grid) {
+    const bool vec_rows = aligned16 && (a.P % 4) == 0 && rows_fit_grid;
+    const bool vec_flat = aligned16 && (a.n_per_cycle % 4) == 0 && !magwarp;
+    // One CTA per row slice only pays off for long rows; spectrogram rows (128..250 columns) are
+    // handled as slices of the cycle's flat plane, 1024 vectors per CTA.
+    const bool long_rows = a.P >= 2048;
+    if (vec_rows && (long_rows || !vec_flat)) {
         a.nvec = a.n_per_cycle / 4;
         return launch_pick<4, true>(a, a.P / 4, magwarp, box, stream);
     }
-    if (!magwarp && aligned16 && (a.n_per_cycle % 4) == 0) {
+    if (vec_flat) {
         a.nvec = a.n_per_cycle / 4;
         return launch_pick<4, false>(a, a.nvec, magwarp, box, stream);
     }
     a.nvec = a.n_per_cycle;
-    if (rows_fit_grid) return launch_pick<1, true>(a, a.P, magwarp, box, stream);
+    if (rows_fit_grid && (long_rows || magwarp)) return launch_pick<1, true>(a, a.P, magwarp, box, stream);
     if (magwarp) return cudaErrorInvalidConfiguration;
     return launch_pick<1, false>(a, a.nvec, magwarp, box, stream);
 }
