@@ -123,6 +123,28 @@ def _stream_handle(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _on_device:
+    """``with _on_device(dev):`` makes ``dev`` the current CUDA device for the launch.  Switching
+    the device costs several microseconds, which shows on the small latency-bound batches, so it
+    is skipped when ``dev`` already is the current device (the normal one-process-per-GPU case)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, device):
+        self.ctx = None
+        if device.index is not None and device.index != torch.cuda.current_device():
+            self.ctx = torch.cuda.device(device)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
+
+
 def version() -> int:
     return load().pcgmix_version()
 
@@ -161,7 +183,7 @@ def mix1d(x, out, frames, mix, lam32, one_minus_lam32, order=None, err_flag=None
     B, C, L = x.shape
     dev = _same_device(x, out, frames, mix, order, err_flag)
     fptr, fstride = _frames_ptr(frames)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = load().pcgmix_mix1d(
             _dev_ptr(x, torch.float32, "x"), _dev_ptr(out, torch.float32, "out"),
             fptr, fstride, _dev_ptr(mix, torch.int32, "mix"),
@@ -184,7 +206,7 @@ def mix1d_magwarp(x, out, frames, mix, lam32, one_minus_lam32, knots, coefmat, k
         raise ValueError("coefmat / knot_pos do not match knot")
     dev = _same_device(x, out, frames, mix, order, err_flag, knots, coefmat, knot_pos)
     fptr, fstride = _frames_ptr(frames)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = load().pcgmix_mix1d_magwarp(
             _dev_ptr(x, torch.float32, "x"), _dev_ptr(out, torch.float32, "out"),
             fptr, fstride, _dev_ptr(mix, torch.int32, "mix"),
@@ -204,7 +226,7 @@ def mix2d(x, out, frames, mix, lam32, one_minus_lam32, tbox=None, h1=0, h2=0, or
     B, Ch, F, T = x.shape
     dev = _same_device(x, out, frames, mix, order, err_flag, tbox)
     fptr, fstride = _frames_ptr(frames)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = load().pcgmix_mix2d(
             _dev_ptr(x, torch.float32, "x"), _dev_ptr(out, torch.float32, "out"),
             fptr, fstride, _dev_ptr(mix, torch.int32, "mix"),
@@ -219,7 +241,7 @@ def segment_dense(states, downsample, cycles, cycle_count, err_flag=None):
     global launch_count
     R, T = states.shape
     dev = _same_device(states, cycles, cycle_count, err_flag)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = load().pcgmix_segment_dense(
             _dev_ptr(states, torch.int8, "states"), R, T, int(downsample),
             _dev_ptr(cycles, torch.int32, "cycles"), cycles.shape[0], _dev_ptr(cycle_count, torch.int32, "cycle_count"),
@@ -232,7 +254,7 @@ def segment_table(positions, codes, rec_offsets, downsample, spec_cols, rec_len,
     global launch_count
     R = rec_offsets.shape[0] - 1
     dev = _same_device(positions, codes, rec_offsets, rec_len, cycles, cycle_count, err_flag)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = load().pcgmix_segment_table(
             _dev_ptr(positions, torch.int32, "positions"), _dev_ptr(codes, torch.int8, "codes"),
             _dev_ptr(rec_offsets, torch.int32, "rec_offsets"), R, int(downsample), int(spec_cols),
@@ -248,7 +270,7 @@ def cut_cycles(signal, cycles, n_cycles, out, n_cycles_dev=None):
     R, C, T = signal.shape
     L = out.shape[-1]
     dev = _same_device(signal, cycles, out, n_cycles_dev)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = load().pcgmix_cut_cycles(
             _dev_ptr(signal, torch.float32, "signal"), R, C, T, _dev_ptr(cycles, torch.int32, "cycles"),
             int(n_cycles), _dev_ptr(n_cycles_dev, torch.int32, "n_cycles_dev", True),
@@ -261,7 +283,7 @@ def duration_features(frames, n, fs, features, err_flag=None):
     global launch_count
     dev = _same_device(frames, features, err_flag)
     fptr, fstride = _frames_ptr(frames)
-    with torch.cuda.device(dev):
+    with _on_device(dev):
         rc = load().pcgmix_duration_features(
             fptr, fstride, int(n), int(fs),
             _dev_ptr(features, torch.float64, "features"), _dev_ptr(err_flag, torch.int32, "err_flag", True),
