@@ -329,3 +329,37 @@ def test_pcgmix_plus_large_batch_sampled():
     curves = orc.warp_curves(length, knots[sample])
     want = (mixed[sample].astype(np.float64) * curves).astype(np.float32)
     assert _rel_err(got[sample], want) <= REL_TOL
+
+
+@pytest.mark.parametrize("shape", [(7, 4, 2500), (3, 2, 10000), (5, 3, 1001), (4, 1, 64 * 250)])
+@pytest.mark.parametrize("magwarp", [False, True])
+def test_output_guard_bands_stay_intact(shape, magwarp):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds WRITES are looked for by hand:
+    the output lives inside a larger buffer filled with a sentinel that must survive the launch."""
+    from pcgmix_b200 import native, spline, synth
+    b, c, length = shape
+    rng = np.random.default_rng(sum(shape))
+    frames = synth.cycle_frames(rng, b, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    mix = rng.permutation(b).astype(np.int32)
+    dev = torch.device("cuda:0")
+    n = b * c * length
+    guard = 4096
+    backing = torch.full((n + 2 * guard,), 12345.0, device=dev)
+    out = backing[guard:guard + n].view(b, c, length)
+    d = torch.from_numpy(data).to(dev)
+    f = torch.from_numpy(frames.astype(np.int32)).to(dev)
+    m = torch.from_numpy(mix).to(dev)
+    lam = np.float32(0.6)
+    if magwarp:
+        knots = rng.normal(1, 0.2, (b, 6, c))
+        pos, mat = spline.magwarp_tables(length, 4)
+        native.mix1d_magwarp(d, out, f, m, lam, np.float32(1) - lam, torch.from_numpy(knots).to(dev),
+                             torch.from_numpy(np.array(mat)).to(dev), torch.from_numpy(np.array(pos)).to(dev), 4)
+    else:
+        native.mix1d(d, out, f, m, lam, np.float32(1) - lam)
+    torch.cuda.synchronize()
+    assert bool((backing[:guard] == 12345.0).all()) and bool((backing[guard + n:] == 12345.0).all())
+    assert not bool((out == 12345.0).any())
+    if not magwarp:
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), orc.mix_batch(data, frames, mix, lam).view(np.uint32))
