@@ -14,6 +14,8 @@
  *   pcgmix_mix1d_magwarp .... the same loop for 'durmixmagwarp' (augmentations.py:902-914)
  *                             fused with magnitude_warp (augmentations.py:674-683, called
  *                             at :924-928 through a device->host->device round trip)
+ *   pcgmix_mix1d_windows .... the same two loops for the '(rand)' displacement variant
+ *                             (augmentations.py:305-337)
  *   pcgmix_mix2d ............ the spectrogram loop (augmentations2d.py:419-426) calling
  *                             mixup_keepdur_multidim_tensors (augmentations2d.py:206-221);
  *                             the optional zero box covers durmixtimemask / durmixfreqmask /
@@ -112,6 +114,19 @@ int pcgmix_mix1d(const float* x, float* out, const int32_t* frames, int32_t fram
  */
 int pcgmix_mix1d_magwarp(const float* x, float* out, const int32_t* frames, int32_t frame_stride,
                          const int32_t* mix, const int32_t* order, float lam, float one_minus_lam,
+                         const double* knots, const double* coefmat, const double* knot_pos,
+                         int32_t K, int32_t B, int32_t C, int32_t L,
+                         int32_t* err_flag, pcgmix_stream_t stream);
+
+/*
+ * PCGmix / PCGmix+ with the blended windows given explicitly instead of derived from the offsets:
+ * windows[b][s] = {start in cycle b, blended length, shift to the partner's sample} for the four
+ * states (int32 [B][4][3]).  This is what the reference's '(rand)' displacement variant needs
+ * (augmentations.py:305-337: the shorter state is placed at a seeded random offset inside the
+ * longer one).  Windows must be ordered and disjoint.  knots == NULL selects plain PCGmix.
+ */
+int pcgmix_mix1d_windows(const float* x, float* out, const int32_t* windows, const int32_t* mix,
+                         const int32_t* order, float lam, float one_minus_lam,
                          const double* knots, const double* coefmat, const double* knot_pos,
                          int32_t K, int32_t B, int32_t C, int32_t L,
                          int32_t* err_flag, pcgmix_stream_t stream);

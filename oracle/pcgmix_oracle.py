@@ -139,7 +139,25 @@ def mix_pair(d1, d2, f1, f2, lam):
     return out
 
 
-def mix_batch(data, frames, mix_indices, lam32):
+def mix_pair_rand(d1, d2, f1, f2, lam, step):
+    """The ``(rand)`` variant of the per-pair mixer (augmentations.py:305-337): the shorter state is
+    blended at a seeded offset inside the longer one.  ``random.Random(step).randint(0, |gap|)`` is
+    drawn from a fresh generator for every state; a longer partner state shifts the READ window,
+    a longer own state shifts the WRITE window."""
+    out = d1.clone() if hasattr(d1, "clone") else d1.copy()
+    for s in range(4):
+        n = min(f1[s + 1] - f1[s], f2[s + 1] - f2[s])
+        gap = (f2[s + 1] - f2[s]) - (f1[s + 1] - f1[s])
+        disp = random.Random(step).randint(0, np.abs(gap))
+        if gap >= 0:
+            a, b = f1[s], f2[s] + disp
+        else:
+            a, b = f1[s] + disp, f2[s]
+        out[..., a:a + n] = out[..., a:a + n] * lam + d2[..., b:b + n] * (1 - lam)
+    return out
+
+
+def mix_batch(data, frames, mix_indices, lam32, rand_step=None):
     """The reference's per-cycle loop (augmentations.py:969-977, augmentations2d.py:419-426)."""
     is_torch = type(data).__module__.split(".")[0] == "torch"
     if is_torch:
@@ -154,7 +172,10 @@ def mix_batch(data, frames, mix_indices, lam32):
     partners = data[mix_indices]
     partner_frames = frames_np[mix_indices]
     for i in range(data.shape[0]):
-        out[i] = mix_pair(data[i], partners[i], frames_np[i], partner_frames[i], lam)
+        if rand_step is None:
+            out[i] = mix_pair(data[i], partners[i], frames_np[i], partner_frames[i], lam)
+        else:
+            out[i] = mix_pair_rand(data[i], partners[i], frames_np[i], partner_frames[i], lam, rand_step)
     return out
 
 
@@ -218,7 +239,7 @@ def parse_magwarp(method: str):
 def pick_pairing(method: str, labels, wav, step: int) -> np.ndarray:
     """Pairing selection in the reference's order (augmentations.py:875-884, 943-952).  The
     modifiers that need files or models absent from the reference repo are not restated."""
-    for unsupported in ("(sameCVD)", "(closestbins=", "(closestknn=", "(salopt", "(rand)"):
+    for unsupported in ("(sameCVD)", "(closestbins=", "(closestknn=", "(salopt"):
         if unsupported in method:
             raise NotImplementedError(f"oracle does not restate the {unsupported} modifier")
     mix = same_label_mix_indices(labels, step)
@@ -255,7 +276,7 @@ def augment_1d(method: str, data, labels, frames, step: int, wav=None):
     mix = pick_pairing(method, labels, wav, step)
     lam = draw_lambda(parse_alpha(method, branch), step)
     lam32 = lambda_as_float32(lam)
-    out = mix_batch(data, frames, mix, lam32)
+    out = mix_batch(data, frames, mix, lam32, rand_step=step if "(rand)" in method else None)
     knots = None
     if branch == "durmixmagwarp":
         sigma, knot = parse_magwarp(method)

@@ -46,11 +46,21 @@ def _device_tables(length: int, knot: int, device):
 
 
 def pcgmix_on_device(data, frames_dev, mix_dev, lam32, one_minus_lam32, knots_dev=None, knot=None,
-                     order_dev=None, out=None, err_flag=None):
+                     order_dev=None, out=None, err_flag=None, windows_dev=None):
     """Device-resident entry: everything already on the GPU (int32 frames / pairing / order,
-    float64 knots).  Launches exactly one kernel on the current stream and returns ``out``."""
+    float64 knots).  Launches exactly one kernel on the current stream and returns ``out``.
+    ``windows_dev`` (B, 4, 3) replaces ``frames_dev`` for the ``(rand)`` displacement variant."""
     if out is None:
         out = torch.empty_like(data)
+    if windows_dev is not None:
+        if knots_dev is None:
+            native.mix1d_windows(data, out, windows_dev, mix_dev, lam32, one_minus_lam32, order=order_dev,
+                                 err_flag=err_flag)
+        else:
+            pos_dev, mat_dev = _device_tables(data.shape[2], knot, data.device)
+            native.mix1d_windows(data, out, windows_dev, mix_dev, lam32, one_minus_lam32, knots_dev, mat_dev, pos_dev,
+                                 knot, order=order_dev, err_flag=err_flag)
+        return out
     if knots_dev is None:
         native.mix1d(data, out, frames_dev, mix_dev, lam32, one_minus_lam32, order=order_dev, err_flag=err_flag)
     else:
@@ -82,7 +92,9 @@ def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RE
     lam = draws.draw_lambda(plan.alpha, step)
     lam32, one_minus = draws.lambda_pair_fp32(lam)
 
-    uploads = [host_frames(frames, batch, length), mix_indices.astype(np.int32),
+    frames_i32 = host_frames(frames, batch, length)
+    uploads = [draws.rand_windows(frames_i32, mix_indices, step) if plan.rand_displacement else frames_i32,
+               mix_indices.astype(np.int32),
                draws.processing_order(mix_indices) if use_processing_order else np.zeros(0, np.int32)]
     if plan.branch == "durmixmagwarp":
         if plan.knot > native.MAX_KNOT:
@@ -90,8 +102,9 @@ def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RE
         uploads.append(draws.draw_knots(batch, plan.knot, channels, plan.sigma))
     on_dev = staging.upload(uploads, data.device)
     knots_dev = on_dev[3] if plan.branch == "durmixmagwarp" else None
-    data_new = pcgmix_on_device(data, on_dev[0], on_dev[1], lam32, one_minus, knots_dev, plan.knot,
-                                order_dev=on_dev[2] if use_processing_order else None)
+    data_new = pcgmix_on_device(data, None if plan.rand_displacement else on_dev[0], on_dev[1], lam32, one_minus,
+                                knots_dev, plan.knot, order_dev=on_dev[2] if use_processing_order else None,
+                                windows_dev=on_dev[0] if plan.rand_displacement else None)
 
     if plan.mix_all:
         # soft labels, as augmentations.py:915-917 / :978-980

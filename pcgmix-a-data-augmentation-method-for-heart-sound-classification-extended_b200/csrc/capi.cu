@@ -105,6 +105,30 @@ int pcgmix_mix1d_magwarp(const float* x, float* out, const int32_t* frames, int3
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix1d_magwarp", e);
 }
 
+int pcgmix_mix1d_windows(const float* x, float* out, const int32_t* windows, const int32_t* mix, const int32_t* order,
+                         float lam, float one_minus_lam, const double* knots, const double* coefmat,
+                         const double* knot_pos, int32_t K, int32_t B, int32_t C, int32_t L, int32_t* err_flag,
+                         pcgmix_stream_t stream) {
+    if (windows == nullptr) return fail("null pointer argument");
+    if (int rc = check_mix_common(x, out, windows, 5, mix, B, C, L)) return rc;
+    const bool magwarp = knots != nullptr;
+    if (magwarp) {
+        if (coefmat == nullptr || knot_pos == nullptr) return fail("null spline argument");
+        if (K < 0 || K > PCGMIX_MAX_KNOT) return fail("knot count outside [0, PCGMIX_MAX_KNOT]");
+        if (L < 2) return fail("magnitude warp needs at least two samples per row");
+    }
+    if (B == 0) return 0;
+    pcgmix::MixArgs a{};
+    a.x = x; a.out = out; a.frames = windows; a.frame_stride = 12; a.windows = windows; a.mix = mix; a.order = order;
+    a.err = err_flag; a.lam = lam; a.one_minus_lam = one_minus_lam; a.B = B; a.R = C; a.P = L; a.F = 1;
+    if (magwarp) {
+        a.knots = knots; a.coefmat = coefmat; a.knot_pos = knot_pos; a.K = K;
+        a.inv_h = static_cast<double>(K + 1) / static_cast<double>(L - 1);
+    }
+    const cudaError_t e = dispatch_mix(a, magwarp, false, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix1d_windows", e);
+}
+
 int pcgmix_mix2d(const float* x, float* out, const int32_t* frames, int32_t frame_stride, const int32_t* mix,
                  const int32_t* order, float lam, float one_minus_lam, int32_t B, int32_t Ch, int32_t F, int32_t T,
                  const int32_t* tbox, int32_t h1, int32_t h2, int32_t* err_flag, pcgmix_stream_t stream) {

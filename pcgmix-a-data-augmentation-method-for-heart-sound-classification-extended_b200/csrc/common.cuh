@@ -19,6 +19,7 @@ struct MixArgs {
     const int32_t* frames;     // row b at frames + b*frame_stride, 5 offsets
     int32_t frame_stride;
     const int32_t* mix;        // [B]
+    const int32_t* windows;    // [B][4][3] {start, blended length, partner shift} or nullptr (derive from frames)
     const int32_t* order;      // [B] or nullptr
     int32_t* err;              // device flag word or nullptr
     float lam;

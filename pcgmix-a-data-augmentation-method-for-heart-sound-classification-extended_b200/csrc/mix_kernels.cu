@@ -82,18 +82,33 @@ __device__ __forceinline__ void build_windows(const MixArgs& a, int b, int4* s_w
     int p = __ldg(a.mix + b);
     const bool bad_partner = static_cast<unsigned>(p) >= static_cast<unsigned>(a.B);
     if (bad_partner) p = b;
-    int f1 = 0, f2 = 0;
-    if (lane < 5) {
-        f1 = __ldg(a.frames + static_cast<size_t>(b) * a.frame_stride + lane);
-        f2 = __ldg(a.frames + static_cast<size_t>(p) * a.frame_stride + lane);
+    int f1 = 0, f2 = 0, n = 0;
+    bool ok;
+    if (a.windows != nullptr) {
+        // explicit windows (the reference's '(rand)' displacement): {start, length, shift} per state
+        if (lane < 4) {
+            const int32_t* w = a.windows + (static_cast<size_t>(b) * 4 + lane) * 3;
+            f1 = __ldg(w);
+            n = __ldg(w + 1);
+            f2 = f1 + __ldg(w + 2);
+        }
+        const int next_lo = __shfl_down_sync(kFullMask, f1, 1);
+        const int limit = (lane < 3) ? next_lo : a.P;
+        ok = (f1 >= 0) & (n >= 0) & (f1 + n <= limit) & (f2 >= 0) & (f2 + n <= a.P);
+    } else {
+        if (lane < 5) {
+            f1 = __ldg(a.frames + static_cast<size_t>(b) * a.frame_stride + lane);
+            f2 = __ldg(a.frames + static_cast<size_t>(p) * a.frame_stride + lane);
+        }
+        const int f1n_ = __shfl_down_sync(kFullMask, f1, 1);
+        const int f2n_ = __shfl_down_sync(kFullMask, f2, 1);
+        const int len1 = f1n_ - f1;
+        const int len2 = f2n_ - f2;
+        ok = (f1 >= 0) & (f2 >= 0) & (len1 >= 0) & (len2 >= 0) & (f1n_ <= a.P) & (f2n_ <= a.P);
+        n = min(len1, len2);
     }
     const int f1n = __shfl_down_sync(kFullMask, f1, 1);
-    const int f2n = __shfl_down_sync(kFullMask, f2, 1);
-    const int len1 = f1n - f1;
-    const int len2 = f2n - f2;
-    const bool ok = (f1 >= 0) & (f2 >= 0) & (len1 >= 0) & (len2 >= 0) & (f1n <= a.P) & (f2n <= a.P);
     const unsigned bad_frames = __ballot_sync(kFullMask, (lane < 4) && !ok);
-    int n = min(len1, len2);
     if (bad_frames != 0u || bad_partner) n = 0;
     // "next start": the column where the state after s begins; P closes the last one
     const int next = (lane < 3) ? f1n : a.P;

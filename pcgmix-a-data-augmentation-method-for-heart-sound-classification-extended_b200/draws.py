@@ -40,7 +40,7 @@ METHODS_2D = ("durratiocutmix", "cutmix", "mixup", "latentmixup", "freqmask", "t
 
 # Pairing / displacement modifiers this implementation does not provide (they need files or
 # trained models that are not part of the reference repository, or are ablations).
-_UNSUPPORTED_MODIFIERS = ("(sameCVD)", "(closestbins=", "(closestknn=", "(salopt", "(rand)")
+_UNSUPPORTED_MODIFIERS = ("(sameCVD)", "(closestbins=", "(closestknn=", "(salopt")
 
 
 @dataclasses.dataclass
@@ -51,6 +51,7 @@ class Plan1D:
     sigma: float = 0.2
     knot: int = 4
     mix_all: bool = False
+    rand_displacement: bool = False
 
 
 @dataclasses.dataclass
@@ -96,7 +97,7 @@ def parse_method_1d(method: str) -> Optional[Plan1D]:
         if mod in method:
             raise NotImplementedError(f"modifier {mod} of {method!r} is not provided by this implementation")
     plan = Plan1D(branch=branch, probability=_probability(method), alpha=_alpha(method, branch),
-                  mix_all="(mixAll)" in method)
+                  mix_all="(mixAll)" in method, rand_displacement="(rand)" in method)
     if branch == "durmixmagwarp" and len(method.split("durmixmagwarp(")) > 1:
         plan.sigma = float(method.split("durmixmagwarp(")[1].split(",")[0])
         plan.knot = int(method.split(",")[1].split(")")[0])
@@ -185,6 +186,28 @@ def mask_geometry(step: int, region_max: float):
     gap = random.Random(step + 131071).uniform(0, region_max)
     frac1 = random.Random(step + 13119).uniform(0, 1 - gap)
     return gap, frac1
+
+
+def rand_windows(frames: np.ndarray, mix: np.ndarray, step: int) -> np.ndarray:
+    """Blended windows of the reference's ``(rand)`` variant (augmentations.py:305-337), as
+    ``(B, 4, 3)`` int32 ``{start in the cycle, blended length, shift to the partner's sample}``.
+
+    Per state the shorter of the two durations is blended, placed at a seeded offset inside the
+    longer one: ``disp = random.Random(step).randint(0, |len2 - len1|)`` from a FRESH generator, so
+    it depends only on the gap; if the partner's state is longer the offset moves the read window
+    in the partner, otherwise it moves the write window in the cycle."""
+    f1 = np.asarray(frames, dtype=np.int64)[:, :5]
+    f2 = f1[np.asarray(mix, dtype=np.int64)]
+    len1, len2 = np.diff(f1, axis=1), np.diff(f2, axis=1)
+    gap = len2 - len1
+    table = {}
+    for g in np.unique(np.abs(gap)).tolist():
+        table[g] = random.Random(step).randint(0, g)
+    disp = np.vectorize(table.__getitem__, otypes=[np.int64])(np.abs(gap))
+    dst = f1[:, :4] + np.where(gap < 0, disp, 0)
+    src = f2[:, :4] + np.where(gap >= 0, disp, 0)
+    out = np.stack([dst, np.minimum(len1, len2), src - dst], axis=2)
+    return np.ascontiguousarray(out.astype(np.int32))
 
 
 def processing_order(mix: np.ndarray) -> np.ndarray:

@@ -38,6 +38,8 @@ SIGNATURES = {
     "pcgmix_mix1d": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _c_i32, _c_i32, _c_i32, _ptr, _ptr],
     "pcgmix_mix1d_magwarp": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _ptr, _ptr, _ptr,
                              _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr],
+    "pcgmix_mix1d_windows": [_ptr, _ptr, _ptr, _ptr, _ptr, _c_f32, _c_f32, _ptr, _ptr, _ptr,
+                             _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr],
     "pcgmix_mix2d": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _c_i32, _c_i32, _c_i32, _c_i32,
                      _ptr, _c_i32, _c_i32, _ptr, _ptr],
     "pcgmix_segment_dense": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr],
@@ -215,6 +217,30 @@ def mix1d_magwarp(x, out, frames, mix, lam32, one_minus_lam32, knots, coefmat, k
             _dev_ptr(knot_pos, torch.float64, "knot_pos"), int(knot), B, C, L,
             _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
     _check(rc, "pcgmix_mix1d_magwarp")
+    launch_count += 1 if B > 0 else 0
+
+
+def mix1d_windows(x, out, windows, mix, lam32, one_minus_lam32, knots=None, coefmat=None, knot_pos=None, knot=0,
+                  order=None, err_flag=None):
+    """PCGmix / PCGmix+ with explicit windows (B, 4, 3) int32; see ``pcgmix_mix1d_windows``."""
+    global launch_count
+    if x.dim() != 3 or out.shape != x.shape:
+        raise ValueError("x and out must be (B, C, L) of equal shape")
+    B, C, L = x.shape
+    if tuple(windows.shape) != (B, 4, 3):
+        raise ValueError(f"windows must be (B, 4, 3), got {tuple(windows.shape)}")
+    if knots is not None and tuple(knots.shape) != (B, knot + 2, C):
+        raise ValueError("knots must be (B, knot+2, C)")
+    dev = _same_device(x, out, windows, mix, order, err_flag, knots, coefmat, knot_pos)
+    with _on_device(dev):
+        rc = load().pcgmix_mix1d_windows(
+            _dev_ptr(x, torch.float32, "x"), _dev_ptr(out, torch.float32, "out"),
+            _dev_ptr(windows, torch.int32, "windows"), _dev_ptr(mix, torch.int32, "mix"),
+            _dev_ptr(order, torch.int32, "order", True), float(lam32), float(one_minus_lam32),
+            _dev_ptr(knots, torch.float64, "knots", True), _dev_ptr(coefmat, torch.float64, "coefmat", True),
+            _dev_ptr(knot_pos, torch.float64, "knot_pos", True), int(knot), B, C, L,
+            _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+    _check(rc, "pcgmix_mix1d_windows")
     launch_count += 1 if B > 0 else 0
 
 

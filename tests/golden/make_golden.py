@@ -220,6 +220,20 @@ def main():
          method=np.array("durratiomixup"), step=np.int64(step), data=x, labels=lab, frames=fr, out=out,
          mix=np.asarray(mix, np.int64))
 
+    # ---- '(rand)' displacement variant (added after the fixtures above; kept last so that the
+    # seeded stream that produced them is unchanged) ---------------------------------------------
+    for name, method, step, b, c, length in (
+        ("pcgmix_rand", "(rand)durratiomixup", 15, 9, 2, 1600),
+        ("pcgmixplus_rand", "(rand)durmixmagwarp(0.2,4)", 16, 6, 3, 2500),
+    ):
+        fr = cycle_frames(rng, b, limit=length)
+        x = signals(rng, fr, (c,), length)
+        lab = rng.integers(0, 2, b).astype(np.int64)
+        out, tgt, mix, same = run_1d(ref1, method, step, x, lab, fr)
+        assert not same
+        save(name, entry=np.array("augmentations.augment"), method=np.array(method), step=np.int64(step),
+             data=x, labels=lab, frames=fr, out=out, target=tgt, mix=mix)
+
 
 if __name__ == "__main__":
     main()

@@ -27,7 +27,8 @@ def test_parse_1d_methods():
     for method in ("respiratoryscale(12,20)durratiomixup", "timemask+durratiomixup", "cutmix", "mixup(same)"):
         with pytest.raises(NotImplementedError):
             draws.parse_method_1d(method)
-    for method in ("(rand)durratiomixup", "(sameCVD)durratiomixup", "(saloptenv)durratiomixup", "(closestknn=3)durmixmagwarp(0.2,4)"):
+    assert draws.parse_method_1d("(rand)durratiomixup").rand_displacement
+    for method in ("(sameCVD)durratiomixup", "(saloptenv)durratiomixup", "(closestknn=3)durmixmagwarp(0.2,4)"):
         with pytest.raises(NotImplementedError):
             draws.parse_method_1d(method)
 

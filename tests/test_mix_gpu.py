@@ -53,9 +53,9 @@ def _run_1d(method, step, data, labels, frames, wav=None):
     return out, tgt, mix, d
 
 
-GOLDEN_MIX = ["pcgmix_c4_l2500", "pcgmix_alpha2_prob", "pcgmix_mixall"]
+GOLDEN_MIX = ["pcgmix_c4_l2500", "pcgmix_alpha2_prob", "pcgmix_mixall", "pcgmix_rand"]
 GOLDEN_WARP = ["pcgmixplus_c4_l2500", "pcgmixplus_default_c2_l800", "pcgmixplus_alpha_k2_oddlen",
-               "pcgmixplus_k7_c3", "pcgmixplus_mixall"]
+               "pcgmixplus_k7_c3", "pcgmixplus_mixall", "pcgmixplus_rand"]
 
 
 @pytest.mark.parametrize("name", GOLDEN_MIX)
@@ -131,7 +131,8 @@ def test_pairs_edge_cases_through_c_abi(golden):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 7), (3, 2, 33), (5, 4, 2500), (9, 3, 1001), (4, 1, 4400), (6, 5, 250)])
-@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)", "durmixmagwarp(0.1,12)", "durmixmagwarp(0.3,0)"])
+@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)", "durmixmagwarp(0.1,12)", "durmixmagwarp(0.3,0)",
+                                    "(rand)durratiomixup", "(rand)durmixmagwarp(0.2,4)"])
 def test_random_shapes_vs_oracle(shape, method):
     from pcgmix_b200 import synth
     b, c, length = shape

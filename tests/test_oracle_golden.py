@@ -12,7 +12,7 @@ from oracle import pcgmix_oracle as orc
 CASES_1D = [
     "pcgmix_c4_l2500", "pcgmixplus_c4_l2500", "pcgmixplus_default_c2_l800",
     "pcgmixplus_alpha_k2_oddlen", "pcgmixplus_k7_c3", "pcgmix_alpha2_prob",
-    "pcgmix_mixall", "pcgmixplus_mixall",
+    "pcgmix_mixall", "pcgmixplus_mixall", "pcgmix_rand", "pcgmixplus_rand",
 ]
 CASES_2D = ["spec_pcgmix_square", "spec_timemask_square", "spec_timemask_default",
             "spec_freqmask_square", "spec_cutout_square", "spec_pcgmix_nonsquare"]
