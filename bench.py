@@ -396,28 +396,31 @@ def run_b200(args):
     # host->device on a side stream while the current one is augmented, and results leave on a third
     # stream, so the two PCIe directions overlap.  Every step still moves its own input and output.
     s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    dev_in = [torch.empty_like(dev_data[0]) for _ in range(2)]
-    in_ready = [torch.cuda.Event() for _ in range(2)]
-    in_free = [torch.cuda.Event() for _ in range(2)]
+    NIN = 3                                                    # input buffers: copies run two steps ahead
+    dev_in = [torch.empty_like(dev_data[0]) for _ in range(NIN)]
+    in_ready = [torch.cuda.Event() for _ in range(NIN)]
+    in_free = [torch.cuda.Event() for _ in range(NIN)]
     out_done = [torch.cuda.Event() for _ in range(2)]
 
     def stage_in(i):
         with torch.cuda.stream(s_in):
-            s_in.wait_event(in_free[i % 2])                    # the augment that read this buffer is done
-            dev_in[i % 2].copy_(host_in[i % len(host_in)], non_blocking=True)
-            in_ready[i % 2].record(s_in)
+            s_in.wait_event(in_free[i % NIN])                  # the augment that read this buffer is done
+            dev_in[i % NIN].copy_(host_in[i % len(host_in)], non_blocking=True)
+            in_ready[i % NIN].record(s_in)
 
     def run_e2e(n, seed0):
         for ev in in_free + out_done:
             ev.record(stream)
         stage_in(0)
+        if n > 1:
+            stage_in(1)
         for i in range(n):
             j = i % len(host_in)
-            if i + 1 < n:
-                stage_in(i + 1)
-            stream.wait_event(in_ready[i % 2])
-            out, _, _, _ = augmentations.augment(a, dev_in[i % 2], ohe_t[j], frames_t[j], wav, _Step(seed0 + i), None, dev, None)
-            in_free[i % 2].record(stream)
+            if i + 2 < n:
+                stage_in(i + 2)
+            stream.wait_event(in_ready[i % NIN])
+            out, _, _, _ = augmentations.augment(a, dev_in[i % NIN], ohe_t[j], frames_t[j], wav, _Step(seed0 + i), None, dev, None)
+            in_free[i % NIN].record(stream)
             done = torch.cuda.Event()
             done.record(stream)
             with torch.cuda.stream(s_out):
@@ -482,7 +485,7 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": E, "ms_per_step": float(te.item()) / E,
                     "h2d_bytes_per_step": in_bytes + small_bytes, "d2h_bytes_per_step": in_bytes + B * 8,
                     "api": "pcgmix_b200.augmentations.augment (host draws + 1 kernel) inside a prefetching loop: pinned host in/out, "
-                           "H2D of step k+1 and D2H of step k-1 on side streams"},
+                           "H2D of steps k+1, k+2 and D2H of step k-1 on side streams"},
             "gpu_launches": gpu_launches, "gpu_launches_e2e": e2e_launches,
             "clocks": clocks,
         }

@@ -184,6 +184,25 @@ int pcgmix_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T,
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,
                              double* features, int32_t* err_flag, pcgmix_stream_t stream);
 
+/*
+ * Copy `bytes` (multiple of 4, 4-byte-aligned pointers) between device memory and PINNED host memory
+ * (either direction) with a small kernel that reaches the host buffer through unified addressing,
+ * instead of with a copy engine.  Used for the per-step tables (offsets, pairing, knots; ~1 MB up)
+ * and the class ids (down) so that they do not queue behind the large batch copies a prefetching
+ * loader keeps in flight on the copy engines.  Enqueued on `stream`.
+ */
+int pcgmix_copy_small(void* dst, const void* src, int64_t bytes, pcgmix_stream_t stream);
+
+/*
+ * HOST helper (no CUDA): the pairing draw.  For every group g (group[i] in [0, n_groups)), with
+ * members idx in ascending order, mix[idx] = random.Random(seed).sample(idx, len(idx)) exactly as
+ * CPython computes it (MT19937, init_by_array seeding, _randbelow, pool algorithm) — the reference's
+ * get_same_label_mix_indices / get_same_wav_mix_indices / get_same_dataset_mix_indices
+ * (augmentations.py:500-556).  seed must be >= 0.
+ */
+int pcgmix_host_group_permutation(const int64_t* group, int64_t n, int64_t n_groups, uint64_t seed,
+                                  int64_t* mix);
+
 #ifdef __cplusplus
 }
 #endif

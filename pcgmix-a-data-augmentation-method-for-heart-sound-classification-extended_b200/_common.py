@@ -19,10 +19,31 @@ def require_cuda_batch(data, ndim: int, what: str):
     return data if data.is_contiguous() else data.contiguous()
 
 
+_label_slots = {}
+
+
 def labels_from_one_hot(target_ohe) -> np.ndarray:
     """Class id per cycle, as the reference recovers it (augmentations.py:501): arg-max of the
-    one-hot target, read back to the host (one small device->host copy per step)."""
-    return target_ohe.max(1, keepdim=True)[1].cpu().detach().numpy().reshape(-1)
+    one-hot target, read back to the host.  On a CUDA tensor the read-back is a tiny kernel writing
+    into pinned host memory followed by an event wait, not a ``.cpu()`` copy: a copy-engine transfer
+    would wait behind any large device->host copy in flight (results of the previous step)."""
+    idx = target_ohe.max(1, keepdim=True)[1].reshape(-1)
+    if not idx.is_cuda:
+        return idx.detach().numpy()
+    from . import native
+    idx = idx.to(torch.int64).contiguous()
+    n = idx.shape[0]
+    key = (idx.device.index, n)
+    slot = _label_slots.get(key)
+    if slot is None:
+        if len(_label_slots) > 16:
+            _label_slots.clear()
+        slot = (torch.empty(n, dtype=torch.int64, pin_memory=True), torch.cuda.Event())
+        _label_slots[key] = slot
+    native.copy_small(slot[0], idx, n * 8)
+    slot[1].record(torch.cuda.current_stream(idx.device))
+    slot[1].synchronize()
+    return slot[0].numpy().copy()
 
 
 def host_frames(frames, batch: int, limit: int) -> np.ndarray:

@@ -41,6 +41,16 @@ int check_mix_common(const float* x, float* out, const int32_t* frames, int32_t 
     return 0;
 }
 
+// Small host->device upload done by SMs reading pinned host memory through UVA instead of by a
+// copy engine: the per-step tables (~1 MB) must not queue behind the 164 MB batch copies that a
+// prefetching loader keeps in flight on the same host->device engine.
+template <typename T>
+__global__ void upload_kernel(const T* __restrict__ src, T* __restrict__ dst, long long n) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        dst[i] = src[i];
+}
+
 }  // namespace
 
 extern "C" {
@@ -73,6 +83,25 @@ int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, i
     g_tuning.consumer_threads = consumer_threads;
     g_tuning.debug = debug;
     return 0;
+}
+
+int pcgmix_copy_small(void* dst, const void* src, int64_t bytes, pcgmix_stream_t stream) {
+    if (bytes < 0 || (bytes > 0 && (dst == nullptr || src == nullptr))) return fail("bad copy argument");
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src) | static_cast<uintptr_t>(bytes);
+    if (bits & 3u) return fail("copy needs 4-byte aligned pointers and size");
+    if (bytes == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if ((bits & 15u) == 0) {
+        const long long n = bytes / 16;
+        const int blocks = static_cast<int>(n / 256 + 1 > 64 ? 64 : n / 256 + 1);
+        upload_kernel<int4><<<blocks, 256, 0, st>>>(static_cast<const int4*>(src), static_cast<int4*>(dst), n);
+    } else {
+        const long long n = bytes / 4;
+        const int blocks = static_cast<int>(n / 256 + 1 > 64 ? 64 : n / 256 + 1);
+        upload_kernel<int><<<blocks, 256, 0, st>>>(static_cast<const int*>(src), static_cast<int*>(dst), n);
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_copy_small", e);
 }
 
 int pcgmix_mix1d(const float* x, float* out, const int32_t* frames, int32_t frame_stride, const int32_t* mix,

@@ -136,6 +136,21 @@ def gate(step: int) -> float:
 
 
 def _grouped_permutation(keys: Sequence, step: int) -> np.ndarray:
+    """Seeded permutation inside every group of equal keys.  Uses the C++ replay of CPython's
+    ``random.Random(step).sample`` from the native library (20x faster than the Python loop, held
+    bit-equal to it by tests); falls back to CPython itself if the library cannot be loaded or the
+    seed is negative (this is host logic — the GPU kernels have no such fallback)."""
+    if isinstance(step, (int, np.integer)) and step >= 0:
+        try:
+            from . import native
+            _, inverse = np.unique(np.asarray(keys), return_inverse=True)
+            return native.host_group_permutation(inverse.reshape(-1), int(inverse.max()) + 1 if inverse.size else 0, int(step))
+        except (native.NativeLibraryError, OSError):
+            pass
+    return _grouped_permutation_python(keys, step)
+
+
+def _grouped_permutation_python(keys: Sequence, step: int) -> np.ndarray:
     groups = {}
     for i, k in enumerate(keys):
         groups.setdefault(k, []).append(i)

@@ -46,6 +46,8 @@ SIGNATURES = {
     "pcgmix_segment_table": [_ptr, _ptr, _ptr, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_cut_cycles": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _c_i32, _ptr],
     "pcgmix_duration_features": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
+    "pcgmix_copy_small": [_ptr, _ptr, ctypes.c_int64, _ptr],
+    "pcgmix_host_group_permutation": [_ptr, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, _ptr],
 }
 
 _lib = None
@@ -145,6 +147,33 @@ class _on_device:
         if self.ctx is not None:
             self.ctx.__exit__(*exc)
         return False
+
+
+def copy_small(dst, src, nbytes: int):
+    """Small copy between device memory and pinned host memory (either direction) done by a kernel
+    instead of a copy engine (see ``pcgmix_copy_small``); enqueued on the current stream of the
+    CUDA tensor's device."""
+    global launch_count
+    cuda_t, host_t = (dst, src) if dst.is_cuda else (src, dst)
+    if not cuda_t.is_cuda or host_t.is_cuda or not host_t.is_pinned():
+        raise RuntimeError("copy_small needs one CUDA tensor and one pinned host tensor")
+    dev = cuda_t.device
+    with _on_device(dev):
+        rc = load().pcgmix_copy_small(dst.data_ptr(), src.data_ptr(), int(nbytes), _stream_handle(dev))
+    _check(rc, "pcgmix_copy_small")
+    launch_count += 1 if nbytes > 0 else 0
+
+
+def host_group_permutation(group_ids, n_groups: int, seed: int):
+    """``mix[idx_g] = random.Random(seed).sample(idx_g, len(idx_g))`` for every group, computed by
+    the C++ replay of CPython's algorithm (host code, no GPU involved)."""
+    import numpy as np
+    g = np.ascontiguousarray(group_ids, dtype=np.int64)
+    mix = np.arange(g.shape[0], dtype=np.int64)
+    rc = load().pcgmix_host_group_permutation(g.ctypes.data, g.shape[0], int(n_groups), int(seed), mix.ctypes.data)
+    if rc != 0:
+        raise RuntimeError("pcgmix_host_group_permutation: bad arguments")
+    return mix
 
 
 def version() -> int:

@@ -1,7 +1,7 @@
 """Host -> device upload of the small per-step arrays (frames, pairing, order, knots).
 
-All arrays of one step are packed into ONE pinned host buffer and moved with ONE asynchronous
-copy on the current stream; the device side is one allocation sliced into typed views.  No
+All arrays of one step are packed into ONE pinned host buffer and moved with ONE small kernel on
+the current stream (it reads the pinned buffer through unified addressing); the device side is one allocation sliced into typed views.  No
 ``cudaMalloc`` per call (PyTorch's caching allocator), no host synchronisation except when a
 pinned slot is about to be reused while its previous copy is still in flight (a ring of slots
 makes that rare).
@@ -12,6 +12,8 @@ from typing import List, Sequence
 
 import numpy as np
 import torch
+
+from . import native
 
 _ALIGN = 16
 _RING = 4
@@ -48,13 +50,15 @@ class Uploader:
             total = (total + _ALIGN - 1) // _ALIGN * _ALIGN
             offsets.append(total)
             total += a.nbytes
-        total = max(total, _ALIGN)
+        total = (max(total, _ALIGN) + _ALIGN - 1) // _ALIGN * _ALIGN
         slot = self._slot(device, total)
         host = slot.buf.numpy()
         for a, off in zip(arrays, offsets):
             host[off:off + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
         dev_buf = torch.empty(total, dtype=torch.uint8, device=device)
-        dev_buf.copy_(slot.buf[:total], non_blocking=True)
+        # by a kernel reading the pinned buffer, not by the copy engine: a prefetching loader keeps
+        # large batch copies in flight on that engine and this upload must not wait behind them
+        native.copy_small(dev_buf, slot.buf, total)
         if slot.event is None:
             slot.event = torch.cuda.Event()
         slot.event.record(torch.cuda.current_stream(device))

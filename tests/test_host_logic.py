@@ -172,3 +172,21 @@ def test_product_code_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_native_pairing_replays_cpython_random_sample():
+    """The C++ host helper must give exactly CPython's random.Random(seed).sample per group."""
+    if not os.path.exists(build_native.LIB_PATH):
+        pytest.skip("library not built yet (run __graft_entry__.build())")
+    rng = np.random.default_rng(12)
+    for trial in range(400):
+        n = int(rng.integers(1, 700))
+        keys = rng.integers(0, int(rng.integers(1, 6)), n)
+        seed = int(rng.integers(0, 2 ** 45)) if trial % 4 == 0 else trial
+        got = draws._grouped_permutation(keys.tolist(), seed)
+        want = draws._grouped_permutation_python(keys.tolist(), seed)
+        assert np.array_equal(got, want), (trial, n, seed)
+    # n = 1 groups, string keys, and the oracle's own pairing
+    assert np.array_equal(draws._grouped_permutation(["x"], 3), [0])
+    labels = rng.integers(0, 2, 4096)
+    assert np.array_equal(draws.same_label_pairing(labels, 77), orc.same_label_mix_indices(labels, 77))
