@@ -10,7 +10,7 @@ namespace {
 
 thread_local char g_error[512] = "";
 
-pcgmix::PipelineTuning g_tuning = {1, 0, 0, 0, 0, 0, 0};
+pcgmix::PipelineTuning g_tuning = {1, 0, 0, 0, 0, 0, 0, 0};
 
 cudaError_t dispatch_mix(const pcgmix::MixArgs& a, bool magwarp, bool box, cudaStream_t stream) {
     if (g_tuning.enabled && pcgmix::pipeline_applicable(a, box)) {
@@ -81,7 +81,8 @@ int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, i
     g_tuning.ctas_per_sm = ctas_per_sm;
     g_tuning.pbuf_pct = pbuf_pct;
     g_tuning.consumer_threads = consumer_threads;
-    g_tuning.debug = debug;
+    g_tuning.debug = debug & 0xffff;
+    g_tuning.vec_per_thread = (debug >> 16) & 3;     // bits 16-17 of `debug` carry the vectors-per-thread knob
     return 0;
 }
 

@@ -38,7 +38,6 @@ namespace pcgmix {
 namespace {
 
 constexpr int kMaxStages = 8;
-constexpr int kVecPerThread = 2;
 constexpr int kHeaderBytes = 1024;
 constexpr int kProducerWarps = 2;       // producer warps take alternate items (one warp's instruction stream per
                                         // item, ~600 dependent instructions with the spline set-up, was the bound)
@@ -131,7 +130,7 @@ struct PipeArgs {
     int debug;                 // profiling only: 1 = skip stores, 2 = skip arithmetic, 4 = skip partner copies
 };
 
-template <int NCT, bool MAGWARP>
+template <int NCT, bool MAGWARP, int VPT>
 __global__ void __launch_bounds__(NCT + kHelperThreads, (NCT <= 192 ? 4 : NCT <= 320 ? 3 : 2))
 mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ PipeArgs pa) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -415,7 +414,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             const int t_beg = meta->t_beg;
             const float* pbase = meta->pbase;
 #pragma unroll
-            for (int k = 0; k < kVecPerThread; ++k) {
+            for (int k = 0; k < VPT; ++k) {
                 const int v = ct + k * NCT;
                 if (v < nvec && !(pa.debug & 2)) {
                     const int col = v * 4;                                   // local column
@@ -483,21 +482,21 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     }
 }
 
-template <int NCT>
+template <int NCT, int VPT>
 cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, int grid, size_t smem, bool magwarp, cudaStream_t stream) {
     // opt in to the large dynamic shared-memory carve-out once per kernel instance
     static bool allowed[2] = {false, false};
     if (!allowed[magwarp ? 1 : 0]) {
         const cudaError_t e = magwarp
-            ? cudaFuncSetAttribute(mix_pipeline_kernel<NCT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-            : cudaFuncSetAttribute(mix_pipeline_kernel<NCT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            ? cudaFuncSetAttribute(mix_pipeline_kernel<NCT, true, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+            : cudaFuncSetAttribute(mix_pipeline_kernel<NCT, false, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         allowed[magwarp ? 1 : 0] = true;
     }
     if (magwarp) {
-        mix_pipeline_kernel<NCT, true><<<grid, NCT + kHelperThreads, smem, stream>>>(a, pa);
+        mix_pipeline_kernel<NCT, true, VPT><<<grid, NCT + kHelperThreads, smem, stream>>>(a, pa);
     } else {
-        mix_pipeline_kernel<NCT, false><<<grid, NCT + kHelperThreads, smem, stream>>>(a, pa);
+        mix_pipeline_kernel<NCT, false, VPT><<<grid, NCT + kHelperThreads, smem, stream>>>(a, pa);
     }
     return cudaGetLastError();
 }
@@ -539,7 +538,9 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     pa.pbuf_cap = ((slice_len * pbuf_pct / 100 + 32) + 31) & ~31;
     pa.stages = tune.stages > 0 ? (tune.stages > kMaxStages ? kMaxStages : tune.stages) : 4;
     if (pa.stages < kProducerWarps) pa.stages = kProducerWarps;
-    const size_t stage_bytes = (static_cast<size_t>(pa.slice_cap) + pa.pbuf_cap) * sizeof(float) + sizeof(StageMeta);
+    // only the (K+1)*4 coefficients in use are reserved at the end of the metadata block
+    const size_t meta_bytes = sizeof(StageMeta) - sizeof(double) * (kMaxPieces * 4 - (magwarp ? (a.K + 1) * 4 : 0));
+    const size_t stage_bytes = (static_cast<size_t>(pa.slice_cap) + pa.pbuf_cap) * sizeof(float) + meta_bytes;
     pa.stage_bytes = static_cast<int>((stage_bytes + 127) & ~static_cast<size_t>(127));
     const size_t mat_bytes = magwarp ? static_cast<size_t>(a.K + 1) * 4 * (a.K + 2) * sizeof(double) : 0;
     pa.header_bytes = static_cast<int>((kHeaderBytes + mat_bytes + 127) & ~static_cast<size_t>(127));
@@ -549,7 +550,8 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     if (n_items > 2147483647LL) return cudaErrorInvalidConfiguration;
     pa.n_items = static_cast<int>(n_items);
     pa.debug = tune.debug;
-    const int need = ((slice_len / 4) + kVecPerThread - 1) / kVecPerThread;   // consumer threads with work
+    const int vpt = tune.vec_per_thread == 1 ? 1 : 2;
+    const int need = ((slice_len / 4) + vpt - 1) / vpt;                       // consumer threads with work
     if (need > 448) return cudaErrorInvalidConfiguration;
     int nct = need <= 128 ? 128 : need <= 192 ? 192 : need <= 256 ? 256 : need <= 320 ? 320 : need <= 384 ? 384 : 448;
     if (tune.consumer_threads > nct) {                                   // more (lighter) consumer threads per slice
@@ -568,13 +570,23 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     pa.stepn_rest = static_cast<int>((grid * kProducerWarps) / a.B);
     pa.stepn_slot = static_cast<int>((grid * kProducerWarps) % a.B);
     if (pa.stages < kProducerWarps) return cudaErrorInvalidConfiguration;
+    if (vpt == 1) {
+        switch (nct) {
+            case 128: return launch_nct<128, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+            case 192: return launch_nct<192, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+            case 256: return launch_nct<256, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+            case 320: return launch_nct<320, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+            case 384: return launch_nct<384, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+            default: return launch_nct<448, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        }
+    }
     switch (nct) {
-        case 128: return launch_nct<128>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        case 192: return launch_nct<192>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        case 256: return launch_nct<256>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        case 320: return launch_nct<320>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        case 384: return launch_nct<384>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        default: return launch_nct<448>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 128: return launch_nct<128, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 192: return launch_nct<192, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 256: return launch_nct<256, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 320: return launch_nct<320, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 384: return launch_nct<384, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        default: return launch_nct<448, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
     }
 }
 
