@@ -78,8 +78,10 @@ int pcgmix_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
  *   pbuf_pct      shared-memory budget for staged partner windows, in % of a slice (0 = default);
  *                 slices whose windows do not fit read the partner straight from global memory
  *   consumer_threads  lower bound on consumer threads per CTA (0 = just enough for one slice)
- *   debug         must be 0; non-zero values switch parts of the pipelined kernel off for
- *                 profiling (1 no stores, 2 no arithmetic, 4 no partner staging) and give wrong output
+ *   debug         must be 0 in production.  Bits 0-4 switch parts of the pipelined kernel off for
+ *                 profiling and give WRONG output (1 no stores, 2 no arithmetic, 4 no partner
+ *                 staging, 8 no coefficient set-up, 16 no knot loads); bits 16-17 select the number
+ *                 of 128-bit vectors per consumer thread (0 = default 2, 1 = one; same output)
  * Results do not depend on any of these.
  */
 int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, int32_t ctas_per_sm,
