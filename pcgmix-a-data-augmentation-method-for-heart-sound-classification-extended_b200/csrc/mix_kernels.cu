@@ -38,6 +38,8 @@ namespace pcgmix {
 namespace {
 
 constexpr int kUnroll = 4;          // vectors per thread, all loads issued before first use
+constexpr int kFlatMaxPitch = 2048; // FLAT slices are used for rows shorter than this
+constexpr int kNoBlend = -2147483647 - 1;
 
 template <int VEC> struct Vec;
 template <> struct Vec<4> {
@@ -129,6 +131,10 @@ mix_kernel(const __grid_constant__ MixArgs a) {
     __shared__ __align__(16) double s_coef[MAGWARP ? kMaxPieces * 4 : 2];
     __shared__ double s_kpos[MAGWARP ? kMaxPieces + 1 : 1];
     __shared__ int s_kint[MAGWARP ? kMaxPieces + 1 : 1];
+    // FLAT slices cover many short rows (spectrograms), and nearly every warp holds a vector that
+    // straddles a state start or a row end.  One column table per CTA (shift to the partner's sample,
+    // or kNoBlend) replaces the per-vector state logic: every column is classified once, used R times.
+    __shared__ int s_lut[ROWS ? 1 : kFlatMaxPitch];
 
     const int slot = blockIdx.x;
     const int b = a.order ? __ldg(a.order + slot) : slot;
@@ -184,6 +190,14 @@ mix_kernel(const __grid_constant__ MixArgs a) {
     }
     __syncthreads();
     const int lo1 = s_win[1].x, lo2 = s_win[2].x, lo3 = s_win[3].x;
+    if constexpr (!ROWS) {
+        for (int t = threadIdx.x; t < a.P; t += T) {
+            const int s = (t >= lo1) + (t >= lo2) + (t >= lo3);
+            const int4 w = s_win[s];
+            s_lut[t] = (static_cast<unsigned>(t - w.x) < static_cast<unsigned>(w.y)) ? w.z : kNoBlend;
+        }
+        __syncthreads();
+    }
     const float* __restrict__ par_ptr = a.x + static_cast<size_t>(s_partner) * a.n_per_cycle + static_cast<size_t>(v0) * VEC;
 
     int tb0 = 0, tb1 = 0;
@@ -205,7 +219,21 @@ mix_kernel(const __grid_constant__ MixArgs a) {
         cols[k] = col;
         rows[k] = row;
         live[k] = 0;
-        if (k * T < left) {
+        if constexpr (!ROWS) {
+            if (k * T < left) {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    int t = col + e;
+                    if (t >= a.P) t -= a.P;
+                    const int d = s_lut[t];
+                    other[k][e] = 0.0f;
+                    if (d != kNoBlend) {
+                        other[k][e] = __ldg(par_ptr + k * T * VEC + e + d);
+                        live[k] |= 1 << e;
+                    }
+                }
+            }
+        } else if (k * T < left) {
             const int s = (col >= lo1) + (col >= lo2) + (col >= lo3);
             const int4 w = s_win[s];                                   // {start, blended, shift, next start}
             const int ahead = col - w.x;
@@ -220,8 +248,7 @@ mix_kernel(const __grid_constant__ MixArgs a) {
                 // vector straddles a state start or a row end (or precedes f[0] > 0): per sample
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
-                    int t = col + e;
-                    if (!ROWS && t >= a.P) t -= a.P;
+                    const int t = col + e;
                     const int se = (t >= lo1) + (t >= lo2) + (t >= lo3);
                     const int4 we = s_win[se];
                     other[k][e] = 0.0f;
@@ -362,10 +389,10 @@ cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out)) & 15u) == 0;
     const bool rows_fit_grid = a.R <= 65535;
     const bool vec_rows = aligned16 && (a.P % 4) == 0 && rows_fit_grid;
-    const bool vec_flat = aligned16 && (a.n_per_cycle % 4) == 0 && !magwarp;
+    const bool vec_flat = aligned16 && (a.n_per_cycle % 4) == 0 && !magwarp && a.P <= kFlatMaxPitch;
     // One CTA per row slice only pays off for long rows; spectrogram rows (128..250 columns) are
     // handled as slices of the cycle's flat plane, 1024 vectors per CTA.
-    const bool long_rows = a.P >= 2048;
+    const bool long_rows = a.P > kFlatMaxPitch;
     if (vec_rows && (long_rows || !vec_flat)) {
         a.nvec = a.n_per_cycle / 4;
         return launch_pick<4, true>(a, a.P / 4, magwarp, box, stream);
@@ -377,6 +404,7 @@ cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t
     a.nvec = a.n_per_cycle;
     if (rows_fit_grid && (long_rows || magwarp)) return launch_pick<1, true>(a, a.P, magwarp, box, stream);
     if (magwarp) return cudaErrorInvalidConfiguration;
+    if (a.P > kFlatMaxPitch) return cudaErrorInvalidConfiguration;
     return launch_pick<1, false>(a, a.nvec, magwarp, box, stream);
 }
 
