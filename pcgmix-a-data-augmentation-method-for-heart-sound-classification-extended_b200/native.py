@@ -63,8 +63,9 @@ def library_path() -> str:
     return build_native.LIB_PATH
 
 
-def load(build_if_missing: bool = False):
-    """Load the shared library (once).  Raises ``NativeLibraryError`` if it is not there."""
+def load(build_if_missing: bool = True):
+    """Load the shared library (once).  If it has not been built yet it is compiled in-tree with
+    nvcc first; if that is impossible, raises ``NativeLibraryError`` — there is no other path."""
     global _lib
     if _lib is not None:
         return _lib
@@ -73,11 +74,15 @@ def load(build_if_missing: bool = False):
             return _lib
         path = library_path()
         if not os.path.exists(path):
-            if not build_if_missing:
+            try:
+                if not build_if_missing:
+                    raise RuntimeError("automatic build disabled")
+                build_native.build()
+            except Exception as exc:
                 raise NativeLibraryError(
-                    f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                    "(needs nvcc).  There is no CPU fallback for the PCGmix kernels.")
-            build_native.build()
+                    f"{path} is missing and could not be built ({exc}): build it with "
+                    "`python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc).  "
+                    "There is no CPU fallback for the PCGmix kernels.") from exc
         lib = ctypes.CDLL(path)
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)

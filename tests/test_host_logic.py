@@ -162,7 +162,7 @@ def test_no_cpu_fallback_and_loud_failure_without_library(monkeypatch):
     monkeypatch.setattr(native, "_lib", None)
     monkeypatch.setattr(build_native, "LIB_PATH", "/nonexistent/libpcgmix_b200.so")
     with pytest.raises(native.NativeLibraryError, match="no CPU fallback"):
-        native.load()
+        native.load(build_if_missing=False)
 
 
 def test_product_code_does_not_import_the_oracle():
