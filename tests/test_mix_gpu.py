@@ -364,3 +364,25 @@ def test_output_guard_bands_stay_intact(shape, magwarp):
     assert not bool((out == 12345.0).any())
     if not magwarp:
         assert np.array_equal(out.cpu().numpy().view(np.uint32), orc.mix_batch(data, frames, mix, lam).view(np.uint32))
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1024), (2, 1, 1028), (13, 3, 3584), (5, 2, 3588), (3, 1, 7168), (37, 2, 1536), (2, 70, 1024)])
+@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)", "durmixmagwarp(0.05,30)", "durmixmagwarp(0.2,0)"])
+def test_pipeline_kernel_shape_corners(shape, method):
+    """Smallest / largest single slice, first multi-slice length, one cycle, one channel, many rows,
+    and the extreme knot counts (0 and PCGMIX_MAX_KNOT: 124 coefficients per row, 32 KB matrix)."""
+    from pcgmix_b200 import synth
+    b, c, length = shape
+    rng = np.random.default_rng(b + 7 * c + length)
+    fs = 2000 if length > 3000 else 1000
+    frames = synth.cycle_frames(rng, b, fs=fs, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    labels = rng.integers(0, 2, b)
+    out, _, mix, _ = _run_1d(method, 29, data, labels, frames)
+    want, want_mix, _, _ = orc.augment_1d(method, data.copy(), labels, frames, 29)
+    assert np.array_equal(mix, want_mix)
+    got = out.cpu().numpy()
+    if "magwarp" in method:
+        assert _rel_err(got, want) <= REL_TOL
+    else:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
