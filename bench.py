@@ -69,6 +69,9 @@ def parse_args():
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--pbuf-pct", type=int, default=0)
     ap.add_argument("--consumer-threads", type=int, default=0)
+    ap.add_argument("--no-launch-overlap", action="store_true",
+                    help="serialise consecutive launches (default: consecutive independent steps may overlap their "
+                         "pipeline fill/drain through programmatic dependent launch)")
     ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: 1 no stores, 2 no arithmetic, 4 no partner staging")
     return ap.parse_args()
 
@@ -319,7 +322,8 @@ def run_b200(args):
         data, frames, labels = make_batch(synth.BENCH_SEED + 1000 * rank + i, B, C, L)
         batches.append((data, frames, labels))
     dev_data = [torch.from_numpy(b[0]).to(dev) for b in batches]
-    outs = [torch.empty_like(dev_data[0]) for _ in range(2)]
+    NOUT = 3                                                   # output buffers in rotation
+    outs = [torch.empty_like(dev_data[0]) for _ in range(NOUT)]
     steps_meta = []
     for s in range(W + K):
         data, frames, labels = batches[s % NB]
@@ -338,8 +342,11 @@ def run_b200(args):
         m = steps_meta[s]
         augmentations.pcgmix_on_device(dev_data[s % NB], m["dev"][0], m["dev"][1], m["lam"][0], m["lam"][1],
                                        m["dev"][3] if magwarp else None, plan.knot, order_dev=m["dev"][2],
-                                       out=outs[s % 2])
+                                       out=outs[s % NOUT])
 
+    # consecutive steps are independent (distinct input batches, two alternating output buffers): let
+    # launch k+1 fill its pipeline while launch k drains; the library re-checks buffer disjointness
+    native.set_launch_overlap(not args.no_launch_overlap)
     for s in range(W):
         launch(s)
     torch.cuda.synchronize()
@@ -352,22 +359,44 @@ def run_b200(args):
         sampler.start()
         time.sleep(0.25)
     stream = torch.cuda.current_stream(dev)
-    marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    # With launch overlap, nothing may sit between two launches on the stream (an event record would
+    # re-serialise them), so only the two bracketing events are recorded and the per-launch time is
+    # total / K.  With --no-launch-overlap every launch is bracketed by its own pair of events.
+    per_launch_events = args.no_launch_overlap
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1 if per_launch_events else 2)]
     launches_before = native.launch_count
+    overlap_before = native.overlap_launches()
     t_begin = time.perf_counter()
     marks[0].record(stream)
     for k in range(K):
         launch(W + k)
-        marks[k + 1].record(stream)
+        if per_launch_events:
+            marks[k + 1].record(stream)
+    if not per_launch_events:
+        marks[1].record(stream)
     torch.cuda.synchronize()
     t_end = time.perf_counter()
     gpu_launches = native.launch_count - launches_before
+    overlapped = native.overlap_launches() - overlap_before
+    native.set_launch_overlap(False)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    total_ms = marks[0].elapsed_time(marks[K])
-    per_launch_ms = [marks[k].elapsed_time(marks[k + 1]) for k in range(K)]
+    total_ms = marks[0].elapsed_time(marks[-1])
+    per_launch_ms = ([marks[k].elapsed_time(marks[k + 1]) for k in range(K)] if per_launch_events else [total_ms / K])
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+
+    # the same K steps once more with ordinary stream serialisation and an event pair around every
+    # launch: per-launch statistics, reported next to the headline for comparison
+    serial_ms = per_launch_ms
+    if not per_launch_events:
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        ev[0].record(stream)
+        for k in range(K):
+            launch(W + k)
+            ev[k + 1].record(stream)
+        torch.cuda.synchronize()
+        serial_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(K)]
 
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -472,21 +501,28 @@ def run_b200(args):
                        f"{args.method} on {B} cycles x {C} ch x {L} samples per GPU",
                        "method": args.method, "cycles_per_step_per_gpu": B, "channels": C, "samples": L,
                        "resident_input_batches": NB,
-                       "l2_policy": f"inputs larger than L2: {NB} x {in_bytes / 1e6:.0f} MB input batches + 2 output "
+                       "l2_policy": f"inputs larger than L2: {NB} x {in_bytes / 1e6:.0f} MB input batches + 3 output "
                                     "buffers rotate, every step reads/writes ~330 MB",
                        "cycle_order": "index" if args.no_order else "pairing-chain",
+                       "launch_overlap": "off" if args.no_launch_overlap else
+                       "programmatic dependent launch between consecutive independent steps (buffers checked disjoint)",
                        "kernel": args.kernel, "stages": args.stages, "max_slice": args.max_slice, "ctas_per_sm": args.ctas_per_sm,
                        "sharding": "batches per rank, pairing inside each batch, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": statistics.fmean(bytes_per_launch),
-                         "kernel_ms_mean": statistics.fmean(per_launch_ms), "kernel_ms_median": statistics.median(per_launch_ms),
-                         "kernel_ms_min": min(per_launch_ms)},
+                         "kernel_ms_mean": statistics.fmean(per_launch_ms),
+                         "serialized_launches": {
+                             "kernel_ms_mean": statistics.fmean(serial_ms), "kernel_ms_median": statistics.median(serial_ms),
+                             "kernel_ms_min": min(serial_ms),
+                             "achieved": statistics.fmean(bytes_per_launch) / (statistics.fmean(serial_ms) * 1e-3) / 1e9,
+                             "frac": statistics.fmean(bytes_per_launch) / (statistics.fmean(serial_ms) * 1e-3) / 1e9 / peak,
+                             "cycles_per_s_per_gpu": B / (statistics.fmean(serial_ms) * 1e-3)}},
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": E, "ms_per_step": float(te.item()) / E,
                     "h2d_bytes_per_step": in_bytes + small_bytes, "d2h_bytes_per_step": in_bytes + B * 8,
                     "api": "pcgmix_b200.augmentations.augment (host draws + 1 kernel) inside a prefetching loop: pinned host in/out, "
                            "H2D of steps k+1, k+2 and D2H of step k-1 on side streams"},
-            "gpu_launches": gpu_launches, "gpu_launches_e2e": e2e_launches,
+            "gpu_launches": gpu_launches, "gpu_launches_overlapped": overlapped, "gpu_launches_e2e": e2e_launches,
             "clocks": clocks,
         }
         if cpu is not None:

@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -11,13 +12,6 @@ namespace {
 thread_local char g_error[512] = "";
 
 pcgmix::PipelineTuning g_tuning = {1, 0, 0, 0, 0, 0, 0, 0};
-
-cudaError_t dispatch_mix(const pcgmix::MixArgs& a, bool magwarp, bool box, cudaStream_t stream) {
-    if (g_tuning.enabled && pcgmix::pipeline_applicable(a, box)) {
-        return pcgmix::launch_mix_pipeline(a, magwarp, g_tuning, stream);
-    }
-    return pcgmix::launch_mix(a, magwarp, box, stream);
-}
 
 int fail(const char* what) {
     std::snprintf(g_error, sizeof(g_error), "%s", what);
@@ -49,6 +43,107 @@ __global__ void upload_kernel(const T* __restrict__ src, T* __restrict__ dst, lo
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
         dst[i] = src[i];
+}
+
+
+// ---- launch overlap (programmatic dependent launch) ------------------------------------------------
+// Two consecutive pipelined launches on one stream may overlap (the second fills its pipeline while
+// the first drains) when the caller opted in AND the second launch neither reads what the previous
+// ones write nor writes what they read or write.  The address ranges of the last two launches per
+// stream are kept here for that check; anything else launches with ordinary stream serialisation.
+struct Range { uintptr_t lo, hi; };
+struct LaunchRecord {
+    cudaStream_t stream;
+    bool valid;
+    unsigned long long signature;   // launch geometry of a GPU-filling pipelined grid, 0 otherwise
+    Range reads[6];
+    int n_reads;
+    Range write;
+};
+bool g_overlap_enabled = false;
+long long g_overlap_launches = 0;       // launches issued with the overlap attribute (diagnostics)
+std::mutex g_overlap_mutex;
+LaunchRecord g_history[8][2];          // up to 8 streams, the last two launches of each
+cudaStream_t g_history_stream[8];
+int g_history_used = 0;
+
+bool intersects(const Range& a, const Range& b) { return a.lo < b.hi && b.lo < a.hi; }
+
+Range range_of(const void* p, size_t bytes) {
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p);
+    return Range{lo, p == nullptr ? lo : lo + bytes};
+}
+
+LaunchRecord record_of(const pcgmix::MixArgs& a, bool magwarp, cudaStream_t stream) {
+    LaunchRecord r{};
+    r.stream = stream;
+    r.valid = true;
+    const size_t cyc = static_cast<size_t>(a.B) * a.R * a.P * sizeof(float);
+    r.write = range_of(a.out, cyc);
+    int n = 0;
+    r.reads[n++] = range_of(a.x, cyc);
+    r.reads[n++] = range_of(a.frames, static_cast<size_t>(a.B) * a.frame_stride * 4);
+    r.reads[n++] = range_of(a.mix, static_cast<size_t>(a.B) * 4);
+    r.reads[n++] = range_of(a.order, static_cast<size_t>(a.B) * 4);
+    if (magwarp) r.reads[n++] = range_of(a.knots, static_cast<size_t>(a.B) * (a.K + 2) * a.R * 8);
+    r.n_reads = n;
+    return r;
+}
+
+bool conflicts(const LaunchRecord& prev, const LaunchRecord& next) {
+    if (intersects(prev.write, next.write)) return true;
+    for (int i = 0; i < next.n_reads; ++i)
+        if (intersects(prev.write, next.reads[i])) return true;
+    for (int i = 0; i < prev.n_reads; ++i)
+        if (intersects(next.write, prev.reads[i])) return true;
+    return false;
+}
+
+// Decide whether this launch may overlap the previous one on its stream (buffers disjoint from the last
+// two launches, caller opted in) and remember it; returns the previous launch's geometry signature.
+bool overlap_decision(const LaunchRecord& now, bool pipelined, unsigned long long* previous_signature) {
+    std::lock_guard<std::mutex> lock(g_overlap_mutex);
+    int slot = -1;
+    for (int i = 0; i < g_history_used; ++i)
+        if (g_history_stream[i] == now.stream) slot = i;
+    if (slot < 0) {
+        slot = g_history_used < 8 ? g_history_used++ : 0;
+        g_history_stream[slot] = now.stream;
+        g_history[slot][0].valid = g_history[slot][1].valid = false;
+    }
+    LaunchRecord* h = g_history[slot];
+    bool ok = g_overlap_enabled && pipelined && h[0].valid;          // h[0]: previous launch, h[1]: the one before
+    if (ok && conflicts(h[0], now)) ok = false;
+    if (ok && h[1].valid && conflicts(h[1], now)) ok = false;
+    *previous_signature = h[0].valid ? h[0].signature : 0ull;
+    h[1] = h[0];
+    h[0] = now;
+    h[0].valid = false;                                               // until its geometry is known (set_signature)
+    h[0].signature = 0ull;
+    return ok;
+}
+
+void set_signature(cudaStream_t stream, unsigned long long signature, bool overlapped) {
+    std::lock_guard<std::mutex> lock(g_overlap_mutex);
+    for (int i = 0; i < g_history_used; ++i) {
+        if (g_history_stream[i] != stream) continue;
+        g_history[i][0].signature = signature;
+        g_history[i][0].valid = signature != 0ull;                    // only GPU-filling pipelined grids can be overlapped
+        if (overlapped) ++g_overlap_launches;
+    }
+}
+
+cudaError_t dispatch_mix(const pcgmix::MixArgs& a, bool magwarp, bool box, cudaStream_t stream) {
+    const bool pipelined = g_tuning.enabled && pcgmix::pipeline_applicable(a, box);
+    unsigned long long previous = 0ull;
+    const bool allowed = overlap_decision(record_of(a, magwarp, stream), pipelined, &previous);
+    if (pipelined) {
+        unsigned long long signature = 0ull;
+        const cudaError_t e = pcgmix::launch_mix_pipeline(a, magwarp, g_tuning, allowed, previous, stream, &signature);
+        set_signature(stream, e == cudaSuccess ? signature : 0ull, allowed && signature != 0ull && signature == previous);
+        return e;
+    }
+    return pcgmix::launch_mix(a, magwarp, box, stream);
 }
 
 }  // namespace
@@ -83,6 +178,15 @@ int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, i
     g_tuning.consumer_threads = consumer_threads;
     g_tuning.debug = debug & 0xffff;
     g_tuning.vec_per_thread = (debug >> 16) & 3;     // bits 16-17 of `debug` carry the vectors-per-thread knob
+    return 0;
+}
+
+long long pcgmix_overlap_launches(void) { return g_overlap_launches; }
+
+int pcgmix_set_launch_overlap(int32_t enable) {
+    std::lock_guard<std::mutex> lock(g_overlap_mutex);
+    g_overlap_enabled = enable != 0;
+    for (int i = 0; i < 8; ++i) g_history[i][0].valid = g_history[i][1].valid = false;
     return 0;
 }
 

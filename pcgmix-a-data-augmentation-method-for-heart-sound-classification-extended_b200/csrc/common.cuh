@@ -62,7 +62,11 @@ struct PipelineTuning {
     int debug;          // profiling only (results become wrong): 1 skip stores, 2 skip arithmetic, 4 skip partner copies
 };
 bool pipeline_applicable(const MixArgs& a, bool box);
-cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const PipelineTuning& tune, cudaStream_t stream);
+// overlap_previous: launch with the programmatic-stream-serialization attribute, i.e. this kernel may start
+// while the previous kernel on the stream (if it is one of ours, which trigger early) is still draining.
+cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const PipelineTuning& tune, bool overlap_previous,
+                                unsigned long long previous_signature, cudaStream_t stream,
+                                unsigned long long* full_grid_signature);
 
 // segment_kernels.cu
 cudaError_t launch_segment_dense(const int8_t* states, int32_t R, int32_t T, int32_t downsample,

@@ -189,6 +189,13 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const int n_it = (pa.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
+    // Programmatic dependent launch: as soon as every CTA of this grid is running, the next launch on
+    // the stream (if the launcher allowed it to overlap) is made ready; its CTAs take over SMs as ours
+    // retire, so its pipeline fills while ours drains.  The launcher only allows this between grids
+    // that fill the whole GPU (so at most two of them are ever in flight) and whose buffers are
+    // disjoint.  Harmless when nothing depends on us.
+    if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     if (threadIdx.x >= NCT + 32) {
         // ===================================== producer warp =====================================
         const int lane = threadIdx.x & 31;
@@ -483,7 +490,8 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
 }
 
 template <int NCT, int VPT>
-cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, int grid, size_t smem, bool magwarp, cudaStream_t stream) {
+cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, int grid, size_t smem, bool magwarp, bool overlap_previous,
+                       cudaStream_t stream) {
     // opt in to the large dynamic shared-memory carve-out once per kernel instance
     static bool allowed[2] = {false, false};
     if (!allowed[magwarp ? 1 : 0]) {
@@ -493,12 +501,18 @@ cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, int grid, size_t sm
         if (e != cudaSuccess) return e;
         allowed[magwarp ? 1 : 0] = true;
     }
-    if (magwarp) {
-        mix_pipeline_kernel<NCT, true, VPT><<<grid, NCT + kHelperThreads, smem, stream>>>(a, pa);
-    } else {
-        mix_pipeline_kernel<NCT, false, VPT><<<grid, NCT + kHelperThreads, smem, stream>>>(a, pa);
-    }
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(NCT + kHelperThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap_previous ? 1 : 0;
+    return magwarp ? cudaLaunchKernelEx(&cfg, mix_pipeline_kernel<NCT, true, VPT>, a, pa)
+                   : cudaLaunchKernelEx(&cfg, mix_pipeline_kernel<NCT, false, VPT>, a, pa);
 }
 
 int g_sm_count = 0;
@@ -510,7 +524,9 @@ bool pipeline_applicable(const MixArgs& a, bool box) {
     return !box && aligned16 && (a.P % 4) == 0 && a.P >= 1024;
 }
 
-cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const PipelineTuning& tune, cudaStream_t stream) {
+cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const PipelineTuning& tune, bool overlap_previous,
+                                unsigned long long previous_signature, cudaStream_t stream,
+                                unsigned long long* full_grid_signature) {
     MixArgs a = base;
     a.n_per_cycle = a.R * a.P;
     if (magwarp) {
@@ -564,6 +580,14 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     per_sm = per_sm < by_threads ? per_sm : by_threads;
     if (tune.ctas_per_sm > 0 && tune.ctas_per_sm < per_sm) per_sm = tune.ctas_per_sm;
     long long grid = static_cast<long long>(g_sm_count) * per_sm;
+    // Geometry signature: non-zero only for a grid that fills the GPU.  Two launches with EQUAL signatures
+    // have the same CTA footprint and CTA count, so the second can only become fully resident after the
+    // first has fully retired: at most two such grids are ever in flight.  Overlap is only allowed then.
+    const unsigned long long signature =
+        grid <= pa.n_items ? ((static_cast<unsigned long long>(smem) << 32) ^ (static_cast<unsigned long long>(nct) << 20) ^
+                              static_cast<unsigned long long>(grid)) : 0ull;
+    if (full_grid_signature != nullptr) *full_grid_signature = signature;
+    if (signature == 0ull || signature != previous_signature) overlap_previous = false;
     if (grid > pa.n_items) grid = pa.n_items;
     pa.step_rest = static_cast<int>(grid / a.B);
     pa.step_slot = static_cast<int>(grid % a.B);
@@ -572,21 +596,21 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     if (pa.stages < kProducerWarps) return cudaErrorInvalidConfiguration;
     if (vpt == 1) {
         switch (nct) {
-            case 128: return launch_nct<128, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-            case 192: return launch_nct<192, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-            case 256: return launch_nct<256, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-            case 320: return launch_nct<320, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-            case 384: return launch_nct<384, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-            default: return launch_nct<448, 1>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+            case 128: return launch_nct<128, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+            case 192: return launch_nct<192, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+            case 256: return launch_nct<256, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+            case 320: return launch_nct<320, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+            case 384: return launch_nct<384, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+            default: return launch_nct<448, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
         }
     }
     switch (nct) {
-        case 128: return launch_nct<128, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        case 192: return launch_nct<192, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        case 256: return launch_nct<256, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        case 320: return launch_nct<320, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        case 384: return launch_nct<384, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
-        default: return launch_nct<448, 2>(a, pa, static_cast<int>(grid), smem, magwarp, stream);
+        case 128: return launch_nct<128, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+        case 192: return launch_nct<192, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+        case 256: return launch_nct<256, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+        case 320: return launch_nct<320, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+        case 384: return launch_nct<384, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+        default: return launch_nct<448, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
     }
 }
 

@@ -34,6 +34,8 @@ SIGNATURES = {
     "pcgmix_version": [],
     "pcgmix_last_error": [],
     "pcgmix_device_info": [_ptr, _ptr, _ptr],
+    "pcgmix_set_launch_overlap": [_c_i32],
+    "pcgmix_overlap_launches": [],
     "pcgmix_set_tuning": [_c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32],
     "pcgmix_mix1d": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _c_i32, _c_i32, _c_i32, _ptr, _ptr],
     "pcgmix_mix1d_magwarp": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _ptr, _ptr, _ptr,
@@ -87,7 +89,8 @@ def load(build_if_missing: bool = True):
         for name, argtypes in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_char_p if name == "pcgmix_last_error" else ctypes.c_int
+            fn.restype = (ctypes.c_char_p if name == "pcgmix_last_error" else
+                          ctypes.c_longlong if name == "pcgmix_overlap_launches" else ctypes.c_int)
         _lib = lib
     return _lib
 
@@ -197,6 +200,16 @@ def set_tuning(use_pipeline: bool = True, stages: int = 0, max_slice: int = 0, c
     _check(load().pcgmix_set_tuning(int(bool(use_pipeline)), int(stages), int(max_slice), int(ctas_per_sm),
                                     int(pbuf_pct), int(consumer_threads), int(debug)),
            "pcgmix_set_tuning")
+
+
+def set_launch_overlap(enable: bool):
+    """Let consecutive, buffer-disjoint PCGmix launches on one stream overlap (programmatic dependent
+    launch); see ``pcgmix_set_launch_overlap`` in the header for what the caller asserts."""
+    _check(load().pcgmix_set_launch_overlap(int(bool(enable))), "pcgmix_set_launch_overlap")
+
+
+def overlap_launches() -> int:
+    return int(load().pcgmix_overlap_launches())
 
 
 def _same_device(*tensors):

@@ -129,7 +129,7 @@ def test_synthetic_generator_shapes():
 def test_library_exports_every_symbol_in_the_header():
     """The C ABI in include/pcgmix_b200.h and the built library / ctypes table must agree."""
     header = open(os.path.join(ROOT, "include", "pcgmix_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|const char\*)\s+(pcgmix_\w+)\s*\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|long long|const char\*)\s+(pcgmix_\w+)\s*\(", header, flags=re.M))
     assert declared == set(native.SIGNATURES), declared ^ set(native.SIGNATURES)
     if not os.path.exists(build_native.LIB_PATH):
         pytest.skip("library not built yet (run __graft_entry__.build())")
@@ -139,7 +139,7 @@ def test_library_exports_every_symbol_in_the_header():
     assert lib.pcgmix_version() >= 100
     # argument counts of the ctypes table follow the header
     for name, args in native.SIGNATURES.items():
-        m = re.search(r"^(?:int|const char\*)\s+" + name + r"\s*\(([^;]*?)\)\s*;", header, flags=re.S | re.M)
+        m = re.search(r"^(?:int|long long|const char\*)\s+" + name + r"\s*\(([^;]*?)\)\s*;", header, flags=re.S | re.M)
         assert m, name
         params = [p for p in m.group(1).replace("\n", " ").split(",") if p.strip() and p.strip() != "void"]
         assert len(params) == len(args), (name, len(params), len(args))
