@@ -409,6 +409,21 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     } else {
         // ===================================== consumer warps ====================================
         const int ct = threadIdx.x;
+        // With one slice per row a thread sees the same columns in every item, so which spline piece
+        // they fall into (and the offset from the piece's knot) is found once, not once per vector.
+        const bool fixed_cols = pa.slices_per_row == 1;
+        int fixed_piece[VPT];
+        double fixed_dt[VPT];
+        if constexpr (MAGWARP) {
+#pragma unroll
+            for (int k = 0; k < VPT; ++k) {
+                const int t = min((ct + k * NCT) * 4, a.P - 4);
+                int piece = min(static_cast<int>(__umulhi(static_cast<unsigned>(t), a.piece_magic)), a.K);
+                while (t >= s_kint[piece + 1]) ++piece;
+                fixed_dt[k] = int_to_double(t) - s_kpos[piece];
+                fixed_piece[k] = (t + 3 < s_kint[piece + 1]) ? piece : -1;      // -1: vector straddles a knot
+            }
+        }
         int stage = 0;
         uint32_t phase = 0;
         for (int it = 0; it < n_it; ++it) {
@@ -451,12 +466,20 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                     }
                     if constexpr (MAGWARP) {
                         const int t = t_beg + col;
-                        int piece = min(static_cast<int>(__umulhi(static_cast<unsigned>(t), a.piece_magic)), a.K);
-                        while (t >= s_kint[piece + 1]) ++piece;
-                        if (__builtin_expect(t + 3 < s_kint[piece + 1], 1)) {
+                        int piece;
+                        double dt;
+                        if (fixed_cols) {
+                            piece = fixed_piece[k];
+                            dt = fixed_dt[k];
+                        } else {
+                            piece = min(static_cast<int>(__umulhi(static_cast<unsigned>(t), a.piece_magic)), a.K);
+                            while (t >= s_kint[piece + 1]) ++piece;
+                            dt = int_to_double(t) - s_kpos[piece];
+                            if (!(t + 3 < s_kint[piece + 1])) piece = -1;
+                        }
+                        if (__builtin_expect(piece >= 0, 1)) {
                             const double2 c01 = *reinterpret_cast<const double2*>(&meta->coef[piece * 4]);
                             const double2 c23 = *reinterpret_cast<const double2*>(&meta->coef[piece * 4 + 2]);
-                            const double dt = int_to_double(t) - s_kpos[piece];
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const double de = dt + static_cast<double>(e);
