@@ -1,0 +1,102 @@
+#!/usr/bin/env python
+"""BASELINE config 4: 1 M synthetic cardiac cycles (245 batches of 4096 x 4 x 2500) through PCGmix+,
+batch-sharded over the GPUs of one box.
+
+    python benchmarks/sweep_1m.py                                   # 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29500 benchmarks/sweep_1m.py                  # N GPUs
+
+Batch k is augmented with seed k on rank k mod N (`pcgmix_b200.sharding`), so the result does not
+depend on N; there is no collective on the path (NCCL only carries the barrier and the MAX over
+ranks).  All of a rank's batches are resident in its HBM (40 GB at N = 1); the signals are drawn on
+the device (the values do not matter for the timing, the offsets and labels are drawn like in
+bench.py), host draws are uploaded before the timed region, consecutive launches may overlap.
+One JSON line per run.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+from pcgmix_b200 import augmentations, draws, native, sharding, staging, synth  # noqa: E402
+
+N_BATCHES, B, C, L, KNOT, SIGMA = 245, 4096, 4, 2500, 4, 0.2
+
+
+def main():
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    native.load()
+    mine = list(sharding.batches_for_rank(N_BATCHES, rank, world))
+    gen = torch.Generator(device=dev)
+    data, metas, m_total = [], [], 0
+    t = torch.arange(L, device=dev)[None, None, :]
+    for k in mine:
+        rng = np.random.default_rng(synth.BENCH_SEED + k)
+        frames = synth.cycle_frames(rng, B, limit=L)
+        labels = rng.integers(0, 2, B)
+        gen.manual_seed(k)
+        x = torch.randn((B, C, L), device=dev, generator=gen)
+        x *= (t < torch.from_numpy(frames[:, 4]).to(dev)[:, None, None])
+        seed = sharding.step_seed(k)
+        mix = draws.same_label_pairing(labels, seed)
+        lam = draws.lambda_pair_fp32(draws.draw_lambda(1, seed))
+        up = staging.upload([frames.astype(np.int32), mix.astype(np.int32), draws.processing_order(mix),
+                             draws.draw_knots(B, KNOT, C, SIGMA)], dev)
+        data.append(x)
+        metas.append((up, lam))
+        m_total += synth.mixed_samples(frames, mix)
+    outs = [torch.empty((B, C, L), device=dev) for _ in range(3)]
+
+    def run(i):
+        up, lam = metas[i]
+        augmentations.pcgmix_on_device(data[i], up[0], up[1], lam[0], lam[1], up[3], KNOT, order_dev=up[2], out=outs[i % 3])
+
+    native.set_launch_overlap(True)
+    for i in range(min(3, len(mine))):
+        run(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(len(mine)):
+        run(i)
+    e1.record()
+    torch.cuda.synchronize()
+    native.set_launch_overlap(False)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    bytes_local = torch.tensor([4.0 * C * (2.0 * L * B * len(mine) + m_total)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(bytes_local, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peak = 6544.7
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        sec = float(ms.item()) * 1e-3
+        gbs = float(bytes_local.item()) / sec / 1e9
+        print(json.dumps({"config": "cfg4: 1M cycles = 245 batches of 4096 x 4 x 2500, durmixmagwarp(0.2,4)",
+                          "n_gpus": world, "cycles": N_BATCHES * B, "seconds": sec, "cycles_per_s": N_BATCHES * B / sec,
+                          "aggregate_algorithmic_GBps": gbs, "frac_of_measured_peak_per_gpu": gbs / world / peak,
+                          "sharding": "batch k -> rank k mod N, seed k, no collective"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
