@@ -338,11 +338,17 @@ def run_b200(args):
         steps_meta.append({"dev": on_dev, "lam": (lam32, oml), "M": synth.mixed_samples(frames, mix)})
     torch.cuda.synchronize()
 
-    def launch(s):
+    # every step's launch is resolved once (pointers, sizes), so that issuing it is one foreign call
+    prepared = []
+    for s in range(W + K):
         m = steps_meta[s]
-        augmentations.pcgmix_on_device(dev_data[s % NB], m["dev"][0], m["dev"][1], m["lam"][0], m["lam"][1],
-                                       m["dev"][3] if magwarp else None, plan.knot, order_dev=m["dev"][2],
-                                       out=outs[s % NOUT])
+        prepared.append(augmentations.prepare_on_device(
+            dev_data[s % NB], m["dev"][0], m["dev"][1], m["lam"][0], m["lam"][1], outs[s % NOUT],
+            m["dev"][3] if magwarp else None, plan.knot, order_dev=m["dev"][2]))
+    stream_handle = torch.cuda.current_stream(dev).cuda_stream
+
+    def launch(s):
+        prepared[s].launch(stream_handle)
 
     # consecutive steps are independent (distinct input batches, two alternating output buffers): let
     # launch k+1 fill its pipeline while launch k drains; the library re-checks buffer disjointness

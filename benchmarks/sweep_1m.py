@@ -60,9 +60,12 @@ def main():
         m_total += synth.mixed_samples(frames, mix)
     outs = [torch.empty((B, C, L), device=dev) for _ in range(3)]
 
+    prepared = [augmentations.prepare_on_device(data[i], up[0], up[1], lam[0], lam[1], outs[i % 3], up[3], KNOT,
+                                                order_dev=up[2]) for i, (up, lam) in enumerate(metas)]
+    handle = torch.cuda.current_stream(dev).cuda_stream
+
     def run(i):
-        up, lam = metas[i]
-        augmentations.pcgmix_on_device(data[i], up[0], up[1], lam[0], lam[1], up[3], KNOT, order_dev=up[2], out=outs[i % 3])
+        prepared[i].launch(handle)
 
     native.set_launch_overlap(True)
     for i in range(min(3, len(mine))):

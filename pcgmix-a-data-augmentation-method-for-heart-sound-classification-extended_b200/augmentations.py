@@ -21,7 +21,7 @@ import torch
 from . import draws, native, spline, staging
 from ._common import host_frames, labels_from_one_hot, require_cuda_batch
 
-__all__ = ["augment", "pcgmix_on_device"]
+__all__ = ["augment", "pcgmix_on_device", "prepare_on_device"]
 
 # Visit the cycles in pairing-chain order (draws.processing_order) so that a cycle read as
 # "partner" is still in L2 when it is read as "itself".  Worth ~3 % of kernel time when batches are
@@ -70,6 +70,20 @@ def pcgmix_on_device(data, frames_dev, mix_dev, lam32, one_minus_lam32, knots_de
         native.mix1d_magwarp(data, out, frames_dev, mix_dev, lam32, one_minus_lam32, knots_dev, mat_dev,
                              pos_dev, knot, order=order_dev, err_flag=err_flag)
     return out
+
+
+def prepare_on_device(data, frames_dev, mix_dev, lam32, one_minus_lam32, out, knots_dev=None, knot=None,
+                      order_dev=None, err_flag=None):
+    """Same launch as :func:`pcgmix_on_device`, with all arguments resolved once: returns an object
+    whose ``launch()`` costs one foreign call.  For sweeps over resident batches."""
+    if knots_dev is None:
+        return native.PreparedMix1D(data, out, frames_dev, mix_dev, lam32, one_minus_lam32, order=order_dev,
+                                    err_flag=err_flag)
+    if knot > native.MAX_KNOT:
+        raise ValueError(f"durmixmagwarp knot={knot} exceeds the supported maximum {native.MAX_KNOT}")
+    pos_dev, mat_dev = _device_tables(data.shape[2], knot, data.device)
+    return native.PreparedMix1D(data, out, frames_dev, mix_dev, lam32, one_minus_lam32, knots_dev, mat_dev, pos_dev,
+                                knot, order=order_dev, err_flag=err_flag)
 
 
 def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RESULTS_ARGS):

@@ -291,6 +291,47 @@ def mix1d_windows(x, out, windows, mix, lam32, one_minus_lam32, knots=None, coef
     launch_count += 1 if B > 0 else 0
 
 
+class PreparedMix1D:
+    """A PCGmix / PCGmix+ launch with every argument resolved once.
+
+    ``mix1d`` / ``mix1d_magwarp`` validate and unpack their tensors on every call (~20 us of Python),
+    which is comparable to the kernel itself when resident batches are swept back to back.  This
+    object does that work at construction and ``launch()`` is a single foreign call on the current
+    stream.  It keeps references to all tensors, so their memory stays valid."""
+
+    def __init__(self, x, out, frames, mix, lam32, one_minus_lam32, knots=None, coefmat=None, knot_pos=None,
+                 knot=0, order=None, err_flag=None):
+        if x.dim() != 3 or out.shape != x.shape:
+            raise ValueError("x and out must be (B, C, L) of equal shape")
+        B, C, L = x.shape
+        self._keep = (x, out, frames, mix, knots, coefmat, knot_pos, order, err_flag)
+        self._device = _same_device(x, out, frames, mix, order, err_flag, knots, coefmat, knot_pos)
+        fptr, fstride = _frames_ptr(frames)
+        lib = load()
+        common = (_dev_ptr(x, torch.float32, "x"), _dev_ptr(out, torch.float32, "out"), fptr, fstride,
+                  _dev_ptr(mix, torch.int32, "mix"), _dev_ptr(order, torch.int32, "order", True),
+                  float(lam32), float(one_minus_lam32))
+        tail = (B, C, L, _dev_ptr(err_flag, torch.int32, "err_flag", True))
+        if knots is None:
+            self._fn, self._args, self._name = lib.pcgmix_mix1d, common + tail, "pcgmix_mix1d"
+        else:
+            if tuple(knots.shape) != (B, knot + 2, C):
+                raise ValueError("knots must be (B, knot+2, C)")
+            spline = (_dev_ptr(knots, torch.float64, "knots"), _dev_ptr(coefmat, torch.float64, "coefmat"),
+                      _dev_ptr(knot_pos, torch.float64, "knot_pos"), int(knot))
+            self._fn, self._args, self._name = lib.pcgmix_mix1d_magwarp, common + spline + tail, "pcgmix_mix1d_magwarp"
+        self._count = 1 if B > 0 else 0
+
+    def launch(self, stream_handle=None):
+        global launch_count
+        if stream_handle is None:
+            stream_handle = torch.cuda.current_stream(self._device).cuda_stream
+        rc = self._fn(*self._args, stream_handle)
+        if rc != 0:
+            _check(rc, self._name)
+        launch_count += self._count
+
+
 def mix2d(x, out, frames, mix, lam32, one_minus_lam32, tbox=None, h1=0, h2=0, order=None, err_flag=None):
     """PCGmix on (B, Ch, F, T) with the optional zero box; see ``pcgmix_mix2d`` in the header."""
     global launch_count

@@ -426,3 +426,29 @@ def test_launch_overlap_keeps_results_and_respects_dependencies():
         assert np.array_equal(cur.cpu().numpy().view(np.uint32), ref.view(np.uint32))
     finally:
         native.set_launch_overlap(False)
+
+
+def test_prepared_launch_matches_plain_call():
+    from pcgmix_b200 import augmentations, draws, native, synth
+    rng = np.random.default_rng(91)
+    b, c, length = 96, 4, 2500
+    dev = torch.device("cuda:0")
+    frames = synth.cycle_frames(rng, b, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    mix = rng.permutation(b).astype(np.int32)
+    knots = rng.normal(1, 0.2, (b, 6, c))
+    d = torch.from_numpy(data).to(dev)
+    f = torch.from_numpy(frames.astype(np.int32)).to(dev)
+    m = torch.from_numpy(mix).to(dev)
+    kn = torch.from_numpy(knots).to(dev)
+    lam = np.float32(0.4)
+    for knots_dev in (None, kn):
+        o1, o2 = torch.empty_like(d), torch.empty_like(d)
+        augmentations.pcgmix_on_device(d, f, m, lam, np.float32(1) - lam, knots_dev, 4, out=o1)
+        prep = augmentations.prepare_on_device(d, f, m, lam, np.float32(1) - lam, o2, knots_dev, 4)
+        before = native.launch_count
+        prep.launch()
+        prep.launch()
+        torch.cuda.synchronize()
+        assert native.launch_count == before + 2
+        assert torch.equal(o1, o2)
