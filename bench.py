@@ -72,6 +72,8 @@ def parse_args():
     ap.add_argument("--no-launch-overlap", action="store_true",
                     help="serialise consecutive launches (default: consecutive independent steps may overlap their "
                          "pipeline fill/drain through programmatic dependent launch)")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="issue the K timed launches from Python instead of replaying them from one CUDA graph")
     ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: 1 no stores, 2 no arithmetic, 4 no partner staging")
     return ap.parse_args()
 
@@ -370,20 +372,43 @@ def run_b200(args):
     # total / K.  With --no-launch-overlap every launch is bracketed by its own pair of events.
     per_launch_events = args.no_launch_overlap
     marks = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1 if per_launch_events else 2)]
+    # The K launches are captured once into a CUDA graph (K kernel nodes, programmatic edges between
+    # them) and replayed: the host issues nothing inside the timed region, so ranks do not drift apart
+    # with host scheduling noise.  --no-graph / --no-launch-overlap launch from Python instead.
+    graph = None
+    if not per_launch_events and not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                capture_handle = torch.cuda.current_stream(dev).cuda_stream
+                for k in range(K):
+                    prepared[W + k].launch(capture_handle)
+            graph.replay()                                      # untimed: instantiate + upload
+            torch.cuda.synchronize()
+        except Exception as exc:                                # capture unsupported: fall back to direct launches
+            print(f"bench: CUDA graph capture failed ({exc!r}); launching directly", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
     launches_before = native.launch_count
     overlap_before = native.overlap_launches()
     t_begin = time.perf_counter()
     marks[0].record(stream)
-    for k in range(K):
-        launch(W + k)
-        if per_launch_events:
-            marks[k + 1].record(stream)
+    if graph is not None:
+        graph.replay()
+    else:
+        for k in range(K):
+            launch(W + k)
+            if per_launch_events:
+                marks[k + 1].record(stream)
     if not per_launch_events:
         marks[1].record(stream)
     torch.cuda.synchronize()
     t_end = time.perf_counter()
-    gpu_launches = native.launch_count - launches_before
-    overlapped = native.overlap_launches() - overlap_before
+    gpu_launches = K if graph is not None else native.launch_count - launches_before
+    overlapped = (K - 1 if graph is not None else native.overlap_launches() - overlap_before)
     native.set_launch_overlap(False)
     if world > 1:
         dist.barrier()
@@ -512,6 +537,7 @@ def run_b200(args):
                        "cycle_order": "index" if args.no_order else "pairing-chain",
                        "launch_overlap": "off" if args.no_launch_overlap else
                        "programmatic dependent launch between consecutive independent steps (buffers checked disjoint)",
+                       "launch_mode": "one CUDA graph of K kernel nodes, replayed" if graph is not None else "K launches from Python",
                        "kernel": args.kernel, "stages": args.stages, "max_slice": args.max_slice, "ctas_per_sm": args.ctas_per_sm,
                        "sharding": "batches per rank, pairing inside each batch, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
