@@ -241,6 +241,26 @@ def recorded_traffic(default_workload: bool):
     return float(best[0]["dram_traffic_bytes_per_launch"]), f"profiles/{best[1]}"
 
 
+def bind_to_gpu_numa_node(gpu_index: int):
+    """Multi-rank runs: keep this rank's host threads (and therefore its first-touched pinned buffers)
+    on the CPU cores NVML reports as local to its GPU.  Best effort; silently skipped if NVML or
+    sched_setaffinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -306,6 +326,7 @@ def run_b200(args):
         raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU port")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    local_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     native.load()
@@ -539,7 +560,8 @@ def run_b200(args):
                        "programmatic dependent launch between consecutive independent steps (buffers checked disjoint)",
                        "launch_mode": "one CUDA graph of K kernel nodes, replayed" if graph is not None else "K launches from Python",
                        "kernel": args.kernel, "stages": args.stages, "max_slice": args.max_slice, "ctas_per_sm": args.ctas_per_sm,
-                       "sharding": "batches per rank, pairing inside each batch, no collective"},
+                       "sharding": "batches per rank, pairing inside each batch, no collective",
+                       "host_affinity": f"rank bound to the {local_cpus} CPU cores local to its GPU" if local_cpus else "default"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": statistics.fmean(bytes_per_launch),
