@@ -452,3 +452,41 @@ def test_prepared_launch_matches_plain_call():
         torch.cuda.synchronize()
         assert native.launch_count == before + 2
         assert torch.equal(o1, o2)
+
+
+@pytest.mark.parametrize("length", [1024, 2500, 3584, 7168])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_arbitrary_monotone_offsets_stress(length, seed):
+    """Offsets drawn uniformly (sorted) from [0, L]: zero-length states, f[0] > 0, f[4] == L, windows
+    cut by slice boundaries of multi-slice rows, windows too large for the staging buffer — against
+    the vectorised oracle, for PCGmix (bit-exact) and PCGmix+ (1e-5)."""
+    from pcgmix_b200 import native, spline
+    rng = np.random.default_rng(1000 * seed + length)
+    b, c = 48, 3
+    frames = np.sort(rng.integers(0, length + 1, size=(b, 5)), axis=1)
+    frames[0] = [0, 0, 0, 0, 0]
+    frames[1] = [0, 0, 0, 0, length]
+    frames[2] = [length, length, length, length, length]
+    frames[3] = [0, length // 4, length // 2, 3 * length // 4, length]
+    frames[4] = [3, 3, length // 3 + 1, length // 3 + 1, length - 1]
+    data = rng.standard_normal((b, c, length)).astype(np.float32)
+    mix = rng.integers(0, b, b).astype(np.int32)            # any mapping, not only permutations
+    dev = torch.device("cuda:0")
+    d = torch.from_numpy(data).to(dev)
+    f = torch.from_numpy(frames.astype(np.int32)).to(dev)
+    m = torch.from_numpy(mix).to(dev)
+    lam = np.float32(rng.uniform(0.05, 0.95))
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = torch.empty_like(d)
+    native.mix1d(d, out, f, m, lam, np.float32(1) - lam, err_flag=err)
+    want = orc.mix_batch_vectorised(data, frames, mix, lam)
+    assert int(err.item()) == 0
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    knots = rng.normal(1, 0.2, (b, 6, c))
+    pos, mat = spline.magwarp_tables(length, 4)
+    native.mix1d_magwarp(d, out, f, m, lam, np.float32(1) - lam, torch.from_numpy(knots).to(dev),
+                         torch.from_numpy(np.array(mat)).to(dev), torch.from_numpy(np.array(pos)).to(dev), 4, err_flag=err)
+    curves = orc.warp_curves(length, knots)
+    want_w = (want.astype(np.float64) * curves).astype(np.float32)
+    assert int(err.item()) == 0
+    assert _rel_err(out.cpu().numpy(), want_w) <= REL_TOL
