@@ -164,6 +164,37 @@ def time_cpu_baseline(method, batch, channels, length, seconds, workers, seed=7)
     return done / elapsed, done, elapsed, per_step
 
 
+def cpu_baseline_cfg1(states, signal, labels, length, reps=5):
+    """CPU-baseline leg of BASELINE config 1 (used by benchmarks/run_configs.py): the oracle's
+    segmentation + cut over dense states, then ``durratiomixup`` per call.  Returns seconds
+    (segmentation + cut once, mix per call)."""
+    import torch
+    from oracle import pcgmix_oracle as orc
+    from oracle import segmentation_oracle as seg_orc
+    t0 = time.perf_counter()
+    cycles, frames = [], []
+    for r in range(states.shape[0]):
+        rel, a0, a1 = seg_orc.cycles_from_dense(states[r])
+        for i in range(len(a0)):
+            cycles.append(np.stack([seg_orc.cut_and_pad(signal[r, c], a0[i], a1[i], length) for c in range(signal.shape[1])]))
+            frames.append(rel[i])
+    t_seg = time.perf_counter() - t0
+    cycles, frames = torch.from_numpy(np.stack(cycles)), torch.from_numpy(np.stack(frames))
+    t0 = time.perf_counter()
+    for rep in range(reps):
+        orc.augment_1d("durratiomixup", cycles, labels, frames, rep)
+    return t_seg, (time.perf_counter() - t0) / reps
+
+
+def cpu_baseline_cfg3(data, labels, frames):
+    """CPU-baseline leg of BASELINE config 3 on a bounded sample: the oracle's 2D per-item loop."""
+    import torch
+    from oracle import pcgmix_oracle as orc
+    t0 = time.perf_counter()
+    orc.augment_2d("durratiomixup", data, labels, torch.from_numpy(np.asarray(frames)), 0)
+    return time.perf_counter() - t0
+
+
 # ----------------------------------------------------------------------------------------------
 # clocks
 # ----------------------------------------------------------------------------------------------

@@ -24,8 +24,7 @@ import torch
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 
-from oracle import pcgmix_oracle as orc  # noqa: E402  (CPU baseline legs only)
-from oracle import segmentation_oracle as seg_orc  # noqa: E402
+import bench  # noqa: E402  (the CPU-baseline legs live in bench.py: the only non-test code that may run oracle/)
 from pcgmix_b200 import augmentations, draws, native, segmentation, spline, staging, synth  # noqa: E402
 
 PEAK = 6544.7
@@ -98,21 +97,7 @@ def main():
     emit("cfg1/durratiomixup (%d cycles x 4 x 4400, frames = cycle table view)" % n_cyc, n_cyc, ms, mn,
          note="latency-bound: %.1f MB per call" % (2 * cycles.numel() * 4 / 1e6))
     # CPU port of the same pipeline (reference structure: Python loops), single process
-    import time
-    st_np, sig_np = states.cpu().numpy(), signal.cpu().numpy()
-    t0 = time.perf_counter()
-    cyc_cpu, fr_cpu = [], []
-    for r in range(n_rec):
-        rel, a0, a1 = seg_orc.cycles_from_dense(st_np[r])
-        for i in range(len(a0)):
-            cyc_cpu.append(np.stack([seg_orc.cut_and_pad(sig_np[r, c], a0[i], a1[i], L1) for c in range(bands)]))
-            fr_cpu.append(rel[i])
-    t_seg = time.perf_counter() - t0
-    cyc_cpu, fr_cpu = np.stack(cyc_cpu), np.stack(fr_cpu)
-    t0 = time.perf_counter()
-    for rep in range(5):
-        orc.augment_1d("durratiomixup", torch.from_numpy(cyc_cpu), labels1, torch.from_numpy(fr_cpu), rep)
-    t_mix = (time.perf_counter() - t0) / 5
+    t_seg, t_mix = bench.cpu_baseline_cfg1(states.cpu().numpy(), signal.cpu().numpy(), labels1, L1)
     emit("cfg1/CPU port: segmentation + cut (once) and durratiomixup per call", n_cyc, t_mix * 1e3, t_mix * 1e3,
          note="segmentation+cut %.1f ms; mix %.2f ms per call on the host (torch-CPU tensors like the reference)" % (t_seg * 1e3, t_mix * 1e3))
     graph = torch.cuda.CUDAGraph()
@@ -173,9 +158,7 @@ def main():
     emit("cfg3/2D durratiomixup 1024 x 1 x 64 x 250 (65.5 MB in)", B3, ms, mn, 4.0 * F3 * (2.0 * T3 * B3 + m3),
          note="working set 131 MB ~ L2 size: partly L2-resident across repetitions")
     n3 = 128                                                   # bounded CPU sample of the same workload
-    t0 = time.perf_counter()
-    orc.augment_2d("durratiomixup", data3[:n3].cpu(), labels3[:n3], torch.from_numpy(frames3[:n3]), 0)
-    t3 = time.perf_counter() - t0
+    t3 = bench.cpu_baseline_cfg3(data3[:n3].cpu(), labels3[:n3], frames3[:n3])
     emit("cfg3/CPU port on a %d-item sample (throughput of the per-item loop is flat in B)" % n3, n3, t3 * 1e3, t3 * 1e3)
     B3b = 8192
     frames3b = synth.spectrogram_frames(rng, B3b, T3)
