@@ -9,8 +9,11 @@ What is shown: the reference's per-step call `augmentations.augment(args, data, 
 wav, step_counter, model, device, EXPERIMENT_ARGS)` (train_model.py:507) served by the B200 kernels,
 with every rank owning its mini-batch and its `step_counter` (all ranks use seed = step, as a
 single-GPU run of the reference would), and `nn.DataParallel` (train_model.py:385) replaced by DDP.
-The network is a compact stand-in with the reference ResNet9-1D's input contract (B, 4, 2500) -> 2
-logits; the reference's own `models.ResNet9` can be dropped in unchanged.  Data is synthetic.
+The network has the reference ResNet9-1D's shape (models.py:520-589: 2 274 626 parameters, 9.1 MB of
+fp32 gradients all-reduced per step); the optimiser step is the reference's (Adam + OneCycleLR +
+gradient value clipping, train_model.py:405-409, 555-569).  Data is synthetic.  Rank 0 prints one
+JSON line: step time, the share of the on-device PCGmix+ call (host wall clock and device time) and
+whole-job cycles/s.
 """
 from __future__ import annotations
 
@@ -29,28 +32,38 @@ sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")
 from pcgmix_b200 import augmentations, synth  # noqa: E402
 
 
-def block(cin, cout, pool):
-    layers = [nn.Conv1d(cin, cout, 3, padding=1, bias=False), nn.BatchNorm1d(cout), nn.ReLU(inplace=True)]
-    if pool:
-        layers.append(nn.MaxPool1d(pool))
-    return nn.Sequential(*layers)
+# (in, out, halve) per convolution stage; a residual pair follows stages 1 and 3.  Widths, the three
+# halvings, the final pool of 4 and the 39 936-wide classifier input are those of the reference's
+# ResNet9 for (4, 2500) inputs (models.py:468-473, 520-531, 589): 2 274 626 parameters.
+STAGES = ((4, 64, False), (64, 128, True), (128, 256, True), (256, 512, True))
+RESIDUAL_AFTER = (1, 3)
+PARAMETERS = 2_274_626
 
 
-class SmallResNet1D(nn.Module):
-    def __init__(self, channels=4, classes=2):
+def conv_unit(cin, cout, halve):
+    unit = [nn.Conv1d(cin, cout, 3, padding=1), nn.BatchNorm1d(cout), nn.ReLU(inplace=True)]
+    return nn.Sequential(*unit, nn.MaxPool1d(2)) if halve else nn.Sequential(*unit)
+
+
+class CycleResNet9(nn.Module):
+    """Consumer of the augmented cycles with the reference ResNet9-1D's shape and size."""
+
+    def __init__(self, classes=2, length=2500):
         super().__init__()
-        self.c1, self.c2 = block(channels, 64, 0), block(64, 128, 2)
-        self.r1 = nn.Sequential(block(128, 128, 0), block(128, 128, 0))
-        self.c3, self.c4 = block(128, 256, 2), block(256, 512, 2)
-        self.r2 = nn.Sequential(block(512, 512, 0), block(512, 512, 0))
-        self.head = nn.Linear(512, classes)
+        self.stages = nn.ModuleList(conv_unit(*spec) for spec in STAGES)
+        self.residuals = nn.ModuleDict({str(i): nn.Sequential(conv_unit(STAGES[i][1], STAGES[i][1], False),
+                                                              conv_unit(STAGES[i][1], STAGES[i][1], False))
+                                        for i in RESIDUAL_AFTER})
+        for _, _, halve in STAGES:
+            length = length // 2 if halve else length
+        self.head = nn.Sequential(nn.MaxPool1d(4), nn.Flatten(), nn.Linear(STAGES[-1][1] * (length // 4), classes))
 
     def forward(self, x):
-        x = self.c2(self.c1(x))
-        x = x + self.r1(x)
-        x = self.c4(self.c3(x))
-        x = x + self.r2(x)
-        return self.head(F.adaptive_max_pool1d(x, 1).flatten(1))
+        for i, stage in enumerate(self.stages):
+            x = stage(x)
+            if str(i) in self.residuals:
+                x = self.residuals[str(i)](x) + x
+        return self.head(x)
 
 
 class StepCounter:
@@ -81,40 +94,57 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(4)
-    model = SmallResNet1D().to(dev)
+    model = CycleResNet9().to(dev)
+    assert sum(p.numel() for p in model.parameters()) == PARAMETERS
     if world > 1:
         model = nn.parallel.DistributedDataParallel(model, device_ids=[local])
     optim = torch.optim.Adam(model.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.OneCycleLR(optim, max_lr=1e-3, total_steps=opt.steps)
     args = Args()
     args.batch_size = opt.batch
     counter = StepCounter()
     rng = np.random.default_rng(100 + rank)                    # every rank draws its own cycles
     wav = ["a0001"] * opt.batch
-    aug_ms, step_ms = [], []
-    for step in range(opt.steps):
+    # a few host batches prepared up front (what the loader's workers would have ready)
+    pool = []
+    for _ in range(4):
         frames = synth.cycle_frames(rng, opt.batch, limit=2500)
-        data = torch.from_numpy(synth.cycle_signals(rng, frames, (4,), 2500)).pin_memory()
-        target = torch.from_numpy(rng.integers(0, 2, opt.batch))
+        pool.append((torch.from_numpy(synth.cycle_signals(rng, frames, (4,), 2500)).pin_memory(),
+                     torch.from_numpy(frames), torch.from_numpy(rng.integers(0, 2, opt.batch))))
+    aug_dev_ms, aug_host_ms, step_ms = [], [], []
+    for step in range(opt.steps):
+        host_data, frames, target = pool[step % len(pool)]
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
-        data = data.to(dev, non_blocking=True)
+        data = host_data.to(dev, non_blocking=True)            # train_model.py:499
         target_ohe = F.one_hot(target, args.num_classes).to(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        data, target_ohe, _, _ = augmentations.augment(args, data, target_ohe, torch.from_numpy(frames), wav, counter,
-                                                       model, dev, None)
+        h0 = time.perf_counter()
+        data, target_ohe, _, _ = augmentations.augment(args, data, target_ohe, frames, wav, counter, model, dev, None)
+        aug_host_ms.append((time.perf_counter() - h0) * 1e3)
         e1.record()
         loss = F.cross_entropy(model(data), target_ohe.float().argmax(1))
-        optim.zero_grad(set_to_none=True)
         loss.backward()                                        # DDP all-reduces the gradients over NCCL here
+        nn.utils.clip_grad_value_(model.parameters(), 0.1)
         optim.step()
+        optim.zero_grad(set_to_none=True)
+        sched.step()
         counter.add()
         torch.cuda.synchronize()
         step_ms.append((time.perf_counter() - t0) * 1e3)
-        aug_ms.append(e0.elapsed_time(e1))
+        aug_dev_ms.append(e0.elapsed_time(e1))
+    t = torch.tensor([float(np.median(step_ms[5:]))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"ranks={world} per-rank batch={opt.batch} steps={opt.steps} loss={loss.item():.4f} "
-              f"median step {np.median(step_ms[3:]):.2f} ms, of which on-device PCGmix+ {np.median(aug_ms[3:]):.3f} ms "
-              f"(cycles/s over all ranks: {world * opt.batch / (np.median(step_ms[3:]) * 1e-3):.0f})")
+        import json
+        ms = float(t.item())
+        print(json.dumps({"config": "cfg5: on-device PCGmix+ -> ResNet9-1D training step, DDP", "n_gpus": world,
+                          "per_rank_batch": opt.batch, "steps": opt.steps, "loss": round(loss.item(), 4),
+                          "median_step_ms_max_over_ranks": ms, "augment_call_host_ms_median": float(np.median(aug_host_ms[5:])),
+                          "augment_device_span_ms_median": float(np.median(aug_dev_ms[5:])),
+                          "cycles_per_s": world * opt.batch / (ms * 1e-3)}))
     if world > 1:
         dist.destroy_process_group()
 
