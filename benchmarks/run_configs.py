@@ -25,7 +25,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 
 import bench  # noqa: E402  (the CPU-baseline legs live in bench.py: the only non-test code that may run oracle/)
-from pcgmix_b200 import augmentations, draws, native, segmentation, spline, staging, synth  # noqa: E402
+from pcgmix_b200 import augmentations, draws, native, resident, segmentation, spline, staging, synth  # noqa: E402
 
 PEAK = 6544.7
 try:
@@ -71,12 +71,56 @@ def prepared_steps(frames, labels, batch, channels, n_steps, magwarp, dev, nb):
     return steps
 
 
+def resident_section(args, dev):
+    C, L = 4, 2500
+    n_rec, Tr, Br = 512, 40000, 4096                            # 328 MB of recordings (>> L2), ~18 k cycles
+    rr = np.random.default_rng(synth.BENCH_SEED + 77)
+    st = torch.from_numpy(synth.dense_states(rr, n_rec, Tr, 1000)).to(dev)
+    sig = torch.from_numpy(rr.standard_normal((n_rec, C, Tr)).astype(np.float32)).to(dev)
+    res = resident.from_dense_states(sig, st, L)
+    frames_all = res.table.cycles[: res.n_cycles, 3:].cpu().numpy().astype(np.int64)
+    out_r = torch.empty((Br, C, L), dtype=torch.float32, device=dev)
+    n_sets = 8
+    sets = []
+    for k in range(n_sets):
+        ids = rr.integers(0, res.n_cycles, Br)
+        mix = draws.same_label_pairing(rr.integers(0, 2, Br), k)
+        lam = draws.lambda_pair_fp32(draws.draw_lambda(1, k))
+        up = staging.upload([ids.astype(np.int32), mix.astype(np.int32), draws.draw_knots(Br, 4, C, 0.2)], dev)
+        f = frames_all[ids]
+        sets.append((up, lam, int(f[:, 4].clip(max=L).sum()), synth.mixed_samples(f, mix)))
+    for magwarp, name in ((True, "durmixmagwarp(0.2,4)"), (False, "durratiomixup")):
+        def fused(i, magwarp=magwarp):
+            up, lam, _, _ = sets[i % n_sets]
+            resident.mix_rows(res, up[0], up[1], lam[0], lam[1], up[2] if magwarp else None, 4, out=out_r)
+
+        def two_step(i, magwarp=magwarp):
+            up, lam, _, _ = sets[i % n_sets]
+            rows = res.table.cycles[up[0].long()]
+            sub = segmentation.CycleTable(rows, res.table.row_ptr, res.table.err_flag)
+            padded = segmentation.cut_cycles(sig, sub, L, Br)
+            augmentations.pcgmix_on_device(padded, rows[:, 3:], up[1], lam[0], lam[1], up[2] if magwarp else None, 4, out=out_r)
+        own = statistics.fmean(s_[2] for s_ in sets)
+        mm = statistics.fmean(s_[3] for s_ in sets)
+        ms, mn = timed(fused, args.reps)
+        emit("resident/%s fused cut+pad+mix from %d recordings x %d x %d, batch %d x %d" % (name, n_rec, C, Tr, Br, L),
+             Br, ms, mn, 4.0 * C * (own + mm + L * Br),
+             note="bytes = 4*C*(sum len1 + sum M + B*L); mean cycle %.0f samples of L=%d" % (own / Br, L))
+        ms2, mn2 = timed(two_step, 50)
+        emit("resident/%s two-step: row gather + cut_cycles + mix kernel (what the fused kernel replaces)" % name,
+             Br, ms2, mn2, note="fused is %.2fx faster" % (ms2 / ms))
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=200)
+    ap.add_argument("--only", default="", choices=["", "resident"])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     native.load()
+    if args.only == "resident":
+        return resident_section(args, dev)
     rng = np.random.default_rng(synth.BENCH_SEED)
 
     # ---------------- cfg1 ----------------
@@ -179,6 +223,7 @@ def main():
     ms, mn = timed(lambda i: native.mix2d(data5, out5, up5[0], up5[1], 0.3, 0.7, order=up5[2]), 50)
     emit("spec128/2D durratiomixup 4096 x 1 x 128 x 128 (268 MB in)", B5, ms, mn,
          4.0 * F5 * (2.0 * T5 * B5 + synth.mixed_samples(frames5, mix5)))
+    resident_section(args, dev)
 
 
 if __name__ == "__main__":

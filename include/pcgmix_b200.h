@@ -29,6 +29,11 @@
  *                             (databuilder.ipynb:627-632, :973-978; :403-411)
  *   pcgmix_duration_features  per-cycle durations, BPM and duration ratios
  *                             (classical.py:245-283)
+ *   pcgmix_mix1d_resident ... cut + zero-pad + PCGmix(+) in one pass over recordings that stay
+ *                             on the device: databuilder.ipynb:627-632, :973-978 (cut, resize),
+ *                             dataloader_physionet.py:43-48 (stacking the padded cycles),
+ *                             train_model.py:499 (batch upload) and the augmentation loops
+ *                             above, without ever materialising the padded (n, C, L) array
  *
  * Host draws (probability gate, pairing, lambda, spline knots) are NOT part of this ABI:
  * they are made on the host from the reference's seed rule and passed in, so both
@@ -43,7 +48,7 @@
 extern "C" {
 #endif
 
-#define PCGMIX_B200_VERSION 100
+#define PCGMIX_B200_VERSION 101
 
 /* bits OR-ed into *err_flag (device int32, may be NULL) by the kernels */
 #define PCGMIX_ERR_BAD_PARTNER   1   /* mix[b] outside [0,B): cycle copied unmixed          */
@@ -196,6 +201,24 @@ int pcgmix_segment_table(const int32_t* positions, const int8_t* codes, const in
 int pcgmix_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T,
                       const int32_t* cycles, int32_t n_cycles, const int32_t* n_cycles_dev,
                       float* out, int32_t L, pcgmix_stream_t stream);
+
+/*
+ * PCGmix / PCGmix+ straight from resident recordings.  Batch slot i is row sel[i] of the cycle
+ * table `cycles` [n_table][8] = {recording, abs_start, abs_stop, f0..f4} (sel == NULL: slot i is
+ * row i, B <= n_table); its samples are signal[recording][c][abs_start + t] for
+ * t < min(abs_stop - abs_start, L) and zero beyond (what pcgmix_cut_cycles would store), its
+ * state offsets are f0..f4 of that row, its partner is slot mix[i].
+ *   out[i] == pcgmix_mix1d(_magwarp)(pcgmix_cut_cycles(signal, rows sel), frames of rows sel, mix)
+ * bit for bit, with out [B][C][L].  knots == NULL: no magnitude warp (PCGmix); otherwise knots
+ * [B][K+2][C], coefmat, knot_pos as for pcgmix_mix1d_magwarp.  `signal` and `cycles` must be
+ * 16-byte aligned.  Rows / recordings / partners out of range and offsets outside [0, L] copy the
+ * cycle unmixed and raise PCGMIX_ERR_BAD_PARTNER / PCGMIX_ERR_BAD_FRAMES in *err_flag.
+ */
+int pcgmix_mix1d_resident(const float* signal, int32_t n_rec, int32_t C, int32_t T,
+                          const int32_t* cycles, int32_t n_table, const int32_t* sel,
+                          const int32_t* mix, const int32_t* order, float lam, float one_minus_lam,
+                          const double* knots, const double* coefmat, const double* knot_pos, int32_t K,
+                          float* out, int32_t B, int32_t L, int32_t* err_flag, pcgmix_stream_t stream);
 
 /* 14 fp64 features per cycle from frames [n][5] int32 (stride `frame_stride` int32 between rows). */
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,

@@ -314,6 +314,35 @@ int pcgmix_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T, cons
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_cut_cycles", e);
 }
 
+int pcgmix_mix1d_resident(const float* signal, int32_t n_rec, int32_t C, int32_t T, const int32_t* cycles,
+                          int32_t n_table, const int32_t* sel, const int32_t* mix, const int32_t* order, float lam,
+                          float one_minus_lam, const double* knots, const double* coefmat, const double* knot_pos,
+                          int32_t K, float* out, int32_t B, int32_t L, int32_t* err_flag, pcgmix_stream_t stream) {
+    if (B < 0 || n_rec < 0 || n_table < 0 || C <= 0 || T < 0 || L <= 0) return fail("bad size argument");
+    if (B == 0) return 0;
+    if (signal == nullptr || cycles == nullptr || mix == nullptr || out == nullptr) return fail("null pointer argument");
+    if (((reinterpret_cast<uintptr_t>(cycles) | reinterpret_cast<uintptr_t>(signal)) & 15u) != 0)
+        return fail("signal and cycles must be 16-byte aligned");
+    if (sel == nullptr && B > n_table) return fail("B exceeds the cycle table and no selection was given");
+    if (!mul_fits_int32(C, L)) return fail("a cycle must hold fewer than 2^31 samples");
+    const bool magwarp = knots != nullptr;
+    if (magwarp) {
+        if (coefmat == nullptr || knot_pos == nullptr) return fail("null spline argument");
+        if (K < 0 || K > PCGMIX_MAX_KNOT) return fail("knot count outside [0, PCGMIX_MAX_KNOT]");
+        if (L < 2) return fail("magnitude warp needs at least two samples per row");
+    }
+    pcgmix::MixArgs a{};
+    a.signal = signal; a.n_rec = n_rec; a.T_sig = T; a.cycles = cycles; a.n_table = n_table; a.sel = sel;
+    a.out = out; a.mix = mix; a.order = order; a.err = err_flag; a.lam = lam; a.one_minus_lam = one_minus_lam;
+    a.B = B; a.R = C; a.P = L; a.F = 1;
+    if (magwarp) {
+        a.knots = knots; a.coefmat = coefmat; a.knot_pos = knot_pos; a.K = K;
+        a.inv_h = static_cast<double>(K + 1) / static_cast<double>(L - 1);
+    }
+    const cudaError_t e = pcgmix::launch_mix_resident(a, magwarp, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix1d_resident", e);
+}
+
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs, double* features,
                              int32_t* err_flag, pcgmix_stream_t stream) {
     if (n < 0 || fs <= 0 || frame_stride < 5) return fail("bad size argument");

@@ -45,10 +45,21 @@ struct MixArgs {
     int32_t F;
     int32_t h1;
     int32_t h2;
+    // resident recordings (mix_resident.cu): cycles are cut out of `signal` on the fly
+    const float* signal;       // [n_rec][R][T_sig]
+    const int32_t* cycles;     // cycle table [n_table][8] {recording, abs_start, abs_stop, f0..f4}
+    const int32_t* sel;        // [B] table row of every batch slot, or nullptr (slot i = row i)
+    int32_t n_table;
+    int32_t n_rec;
+    int32_t T_sig;
+    long long n_sig;           // n_rec*R*T_sig
 };
 
 // mix_kernels.cu — direct-load kernel (any shape)
 cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t stream);
+
+// mix_resident.cu — cut + zero-pad + mix(+warp) in one pass over recordings that stay on the device
+cudaError_t launch_mix_resident(const MixArgs& base, bool magwarp, cudaStream_t stream);
 
 // mix_pipeline.cu — persistent TMA-pipelined kernel (rows of >= 1024 floats, P % 4 == 0, aligned)
 struct PipelineTuning {

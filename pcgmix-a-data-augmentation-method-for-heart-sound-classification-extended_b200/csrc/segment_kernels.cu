@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kSegThreads) offsets_kernel(int32_t* cycle_cou
 // float4 when the output row is 16-byte aligned.
 template <int VEC>
 __global__ void __launch_bounds__(256)
-cut_cycles_kernel(const float* __restrict__ signal, int C, int T, const int32_t* __restrict__ cycles, int n_cycles,
+cut_cycles_kernel(const float* __restrict__ signal, int R, int C, int T, const int32_t* __restrict__ cycles, int n_cycles,
                   const int32_t* __restrict__ n_cycles_dev, float* __restrict__ out, int L) {
     const int n_live = n_cycles_dev ? min(n_cycles, *n_cycles_dev) : n_cycles;
     const long long n_rows = static_cast<long long>(n_live) * C;
@@ -236,8 +236,9 @@ cut_cycles_kernel(const float* __restrict__ signal, int C, int T, const int32_t*
         const int rec = head.x;
         const int start = min(max(head.y, 0), T);
         const int stop = min(max(head.z, start), T);
-        const int n = stop - start;
-        const float* src = signal + (static_cast<size_t>(rec) * C + c) * T + start;
+        // a row naming a recording that does not exist yields an all-zero cycle instead of a wild read
+        const int n = static_cast<unsigned>(rec) < static_cast<unsigned>(R) ? stop - start : 0;
+        const float* src = signal + (static_cast<size_t>(n > 0 ? rec : 0) * C + c) * T + start;
         float* dst = out + static_cast<size_t>(r) * L;
         for (int v = threadIdx.x; v < vec_per_row; v += blockDim.x) {
             float val[VEC];
@@ -333,15 +334,14 @@ cudaError_t launch_segment_table(const int32_t* positions, const int8_t* codes, 
 cudaError_t launch_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T, const int32_t* cycles,
                               int32_t n_cycles, const int32_t* n_cycles_dev, float* out, int32_t L,
                               cudaStream_t stream) {
-    (void)R;
     if (n_cycles == 0 || C == 0 || L == 0) return cudaSuccess;
     const long long rows = static_cast<long long>(n_cycles) * C;
     const unsigned grid = static_cast<unsigned>(rows < (1LL << 20) ? rows : (1LL << 20));
     const bool vec4 = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0);
     if (vec4) {
-        cut_cycles_kernel<4><<<grid, 256, 0, stream>>>(signal, C, T, cycles, n_cycles, n_cycles_dev, out, L);
+        cut_cycles_kernel<4><<<grid, 256, 0, stream>>>(signal, R, C, T, cycles, n_cycles, n_cycles_dev, out, L);
     } else {
-        cut_cycles_kernel<1><<<grid, 256, 0, stream>>>(signal, C, T, cycles, n_cycles, n_cycles_dev, out, L);
+        cut_cycles_kernel<1><<<grid, 256, 0, stream>>>(signal, R, C, T, cycles, n_cycles, n_cycles_dev, out, L);
     }
     return cudaGetLastError();
 }

@@ -1,0 +1,211 @@
+"""Fused cut + pad + PCGmix(+) over resident recordings (``pcgmix_mix1d_resident``) against
+(a) the two-step device path it replaces (``pcgmix_cut_cycles`` then ``pcgmix_mix1d[_magwarp]``,
+bit for bit), and (b) the CPU oracle (cut + pad of the notebook cells, then the reference's
+``augment``): bit-exact for PCGmix, 1e-5 relative for PCGmix+ (north_star's tolerance)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pcgmix_oracle as orc
+from oracle import segmentation_oracle as seg_orc
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5       # north_star: float outputs within 1e-5 relative of the NumPy reference
+
+
+class _Args:
+    def __init__(self, method, batch):
+        self.method, self.batch_size, self.sample_rate, self.num_classes = method, batch, 1000, 2
+
+
+class _Step:
+    def __init__(self, count):
+        self.count = count
+
+
+def _resident(seed, n_rec, channels, t_len, length, fs=1000):
+    from pcgmix_b200 import resident, synth
+    rng = np.random.default_rng(seed)
+    states = synth.dense_states(rng, n_rec, t_len, fs)
+    signal = rng.standard_normal((n_rec, channels, t_len)).astype(np.float32)
+    res = resident.from_dense_states(torch.from_numpy(signal).cuda(), torch.from_numpy(states).cuda(), length)
+    return res, signal, states, rng
+
+
+def _bits(a):
+    return a.view(np.uint32)
+
+
+@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)", "(alpha=0.4)durmixmagwarp(0.3,7)"])
+@pytest.mark.parametrize("n_rec,channels,t_len,length", [
+    (12, 4, 9001, 2500),     # odd recording length: every row starts at a different 16-byte phase
+    (9, 1, 12002, 2500),
+    (6, 3, 8003, 1598),      # L not a multiple of 4: scalar variant
+    (5, 2, 30000, 4400),     # two slices per row
+])
+def test_resident_equals_cut_then_mix(method, n_rec, channels, t_len, length):
+    from pcgmix_b200 import augmentations, resident
+    res, _, _, rng = _resident(n_rec * 7 + channels, n_rec, channels, t_len, length)
+    assert res.n_cycles > 8
+    batch = 2 * res.n_cycles + 3                                  # rows repeat inside the batch
+    ids = rng.integers(0, res.n_cycles, batch)
+    labels = rng.integers(0, 2, batch)
+    ohe = torch.nn.functional.one_hot(torch.from_numpy(labels), 2).cuda()
+    wav = ["a"] * batch
+    for step, ids_arg in ((3, ids), (11, torch.from_numpy(ids).cuda())):
+        got, _, mix, _ = resident.augment(_Args(method, batch), res, ids_arg, ohe, wav, _Step(step), None, "cuda", None)
+        want, _, mix2, _ = augmentations.augment(_Args(method, batch), res.padded(ids), ohe, res.frames_of(ids), wav,
+                                                 _Step(step), None, "cuda", None)
+        res.check()
+        assert np.array_equal(mix, mix2)
+        assert got.shape == (batch, channels, length)
+        assert np.array_equal(_bits(got.cpu().numpy()), _bits(want.cpu().numpy()))
+
+
+@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)"])
+def test_resident_against_cpu_oracle(method):
+    from pcgmix_b200 import resident
+    res, signal, states, rng = _resident(5, 8, 4, 10007, 2500)
+    # CPU: the notebook's cycle rule + cut + pad, then the reference's augment
+    cyc, frames = [], []
+    for r in range(states.shape[0]):
+        rel, a0, a1 = seg_orc.cycles_from_dense(states[r])
+        for i in range(len(a0)):
+            cyc.append(np.stack([seg_orc.cut_and_pad(signal[r, c], a0[i], a1[i], 2500) for c in range(4)]))
+            frames.append(rel[i])
+    cyc, frames = np.stack(cyc), np.stack(frames)
+    assert cyc.shape[0] == res.n_cycles
+    ids = rng.permutation(res.n_cycles)[: res.n_cycles - 1]
+    labels = rng.integers(0, 2, len(ids))
+    want, want_mix, _, _ = orc.augment_1d(method, cyc[ids], labels, frames[ids], 9)
+    ohe = torch.nn.functional.one_hot(torch.from_numpy(labels), 2).cuda()
+    got, _, mix, _ = resident.augment(_Args(method, len(ids)), res, ids, ohe, ["a"] * len(ids), _Step(9), None, "cuda", None)
+    res.check()
+    got = got.cpu().numpy()
+    assert np.array_equal(mix, want_mix)
+    if method == "durratiomixup":
+        assert np.array_equal(_bits(got), _bits(want))
+    else:
+        denom = np.maximum(np.abs(want), np.finfo(np.float32).tiny)
+        assert float(np.max(np.abs(got - want) / denom)) <= REL_TOL
+        assert np.mean(got == want) > 0.999
+
+
+def test_gate_fail_and_unknown_method_return_the_plain_batch():
+    from pcgmix_b200 import resident
+    res, _, _, rng = _resident(1, 4, 2, 9000, 2500)
+    ids = rng.integers(0, res.n_cycles, 10)
+    ohe = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, 2, 10)), 2).cuda()
+    for method, step in (("durratiomixup+0.0", 1), ("base", 1)):
+        out, t, mix, cut = resident.augment(_Args(method, 10), res, ids, ohe, ["a"] * 10, _Step(step), None, "cuda", None)
+        assert mix == [] and cut is None and t is ohe
+        assert torch.equal(out, res.padded(ids))
+
+
+def _hand_made(signal, rows, length):
+    """A resident set around a hand-written cycle table."""
+    from pcgmix_b200 import resident, segmentation
+    dev = torch.device("cuda")
+    table = segmentation.CycleTable(torch.tensor(rows, dtype=torch.int32, device=dev),
+                                    torch.tensor([0, len(rows)], dtype=torch.int32, device=dev),
+                                    torch.zeros(1, dtype=torch.int32, device=dev))
+    return resident.ResidentCycles(torch.from_numpy(signal).cuda(), table, length, len(rows),
+                                   torch.zeros(1, dtype=torch.int32, device=dev))
+
+
+def _two_step(res, mix, lam, knots=None, knot=0):
+    """pcgmix_cut_cycles followed by pcgmix_mix1d(_magwarp) through the direct-load and the pipelined kernel."""
+    from pcgmix_b200 import native
+    from pcgmix_b200.augmentations import pcgmix_on_device
+    padded = res.padded()
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = pcgmix_on_device(padded, res.table.frames[: res.n_cycles], mix, lam[0], lam[1], knots, knot, err_flag=err)
+    return out, int(err.item())
+
+
+@pytest.mark.parametrize("warp", [False, True])
+def test_cycles_touching_the_end_of_the_tensor_and_too_long_cycles(warp):
+    """Rows that end exactly at the last element of a tensor whose size is not a multiple of 4 (the
+    aligned loads must not run past it), a cycle clipped by the end of its recording, and cycles longer
+    than L (offsets outside [0, L]: copied unmixed and flagged, like the two-step path)."""
+    from pcgmix_b200 import draws, resident
+    rng = np.random.default_rng(3)
+    t_len, length = 3001, 1000
+    signal = rng.standard_normal((2, 1, t_len)).astype(np.float32)              # 6002 floats
+    rows = [
+        [1, 2301, 3001, 0, 100, 300, 400, 700],      # ends at the very last element of the tensor
+        [0, 2303, 3001, 0, 120, 280, 410, 698],      # ends at the end of recording 0
+        [1, 5, 905, 0, 90, 350, 460, 900],
+        [0, 2, 1502, 0, 200, 600, 800, 1500],        # longer than L -> flagged, copied
+        [1, 2500, 3400, 0, 100, 400, 500, 900],      # table says 900 samples, the recording has 501: rest is padding
+        [0, 1000, 1000, 0, 0, 0, 0, 0],              # empty cycle
+    ]
+    res = _hand_made(signal, rows, length)
+    mix = torch.tensor([1, 2, 4, 0, 3, 4], dtype=torch.int32, device="cuda")
+    lam = draws.lambda_pair_fp32(0.37)
+    knots = torch.from_numpy(rng.normal(1.0, 0.2, (6, 6, 1))).cuda() if warp else None
+    got = resident.mix_rows(res, None, mix, lam[0], lam[1], knots, 4)
+    want, flag = _two_step(res, mix, lam, knots, 4)
+    assert np.array_equal(_bits(got.cpu().numpy()), _bits(want.cpu().numpy()))
+    assert int(res.err_flag.item()) == flag and flag != 0
+    with pytest.raises(ValueError):
+        res.check()
+
+
+def test_out_of_range_rows_and_partners_are_flagged_not_followed():
+    from pcgmix_b200 import draws, native, resident
+    rng = np.random.default_rng(4)
+    signal = rng.standard_normal((1, 2, 4000)).astype(np.float32)
+    rows = [[0, 0, 900, 0, 100, 400, 500, 900], [0, 1000, 1800, 0, 90, 300, 420, 800], [7, 0, 900, 0, 100, 400, 500, 900]]
+    res = _hand_made(signal, rows, 1000)
+    lam = draws.lambda_pair_fp32(0.5)
+    guard = torch.full((6, 2, 1000), 7.0, device="cuda")
+    out = guard[1:5]
+    sel = torch.tensor([0, 5, 2, 1], dtype=torch.int32, device="cuda")          # row 5 does not exist; row 2 names recording 7
+    mix = torch.tensor([3, 0, 0, 9], dtype=torch.int32, device="cuda")          # partner 9 does not exist
+    resident.mix_rows(res, sel, mix, lam[0], lam[1], out=out)
+    torch.cuda.synchronize()
+    assert int(res.err_flag.item()) & native.ERR_BAD_PARTNER
+    with pytest.raises(IndexError):
+        res.check()
+    assert torch.all(guard[0] == 7.0) and torch.all(guard[5] == 7.0)             # nothing written outside out
+    padded = res.padded()
+    assert torch.equal(out[1], torch.zeros_like(out[1])) and torch.equal(out[2], torch.zeros_like(out[2]))
+    assert torch.equal(out[3], padded[1])                                       # bad partner: own cycle, unmixed
+    want0 = orc.mix_pair(padded[0].cpu().numpy(), padded[1].cpu().numpy(), np.array(rows[0][3:]), np.array(rows[1][3:]),
+                         np.float32(0.5))
+    assert np.array_equal(_bits(out[0].cpu().numpy()), _bits(np.asarray(want0, dtype=np.float32)))
+
+
+def test_full_size_batch_property():
+    """BASELINE-sized batch (4096 cycles x 4 ch x 2500) drawn from resident recordings: outside the
+    blended windows the output is the cut cycle (times the warp curve), padding stays zero for PCGmix."""
+    from pcgmix_b200 import resident
+    res, _, _, rng = _resident(21, 96, 4, 60000, 2500)
+    batch = 4096
+    ids = rng.integers(0, res.n_cycles, batch)
+    labels = rng.integers(0, 2, batch)
+    ohe = torch.nn.functional.one_hot(torch.from_numpy(labels), 2).cuda()
+    got, _, mix, _ = resident.augment(_Args("durratiomixup", batch), res, ids, ohe, ["a"] * batch, _Step(2), None, "cuda", None)
+    res.check()
+    padded = res.padded(ids)
+    frames = res.frames_of(ids).numpy()
+    cols = torch.arange(2500, device="cuda")[None, :]
+    f = torch.from_numpy(frames).cuda()
+    fp = f[torch.from_numpy(mix).cuda()]
+    n = torch.minimum(f[:, 1:] - f[:, :-1], fp[:, 1:] - fp[:, :-1])
+    blended = torch.zeros((batch, 2500), dtype=torch.bool, device="cuda")
+    for s in range(4):
+        blended |= (cols >= f[:, s:s + 1]) & (cols < f[:, s:s + 1] + n[:, s:s + 1])
+    keep = ~blended[:, None, :].expand(-1, 4, -1)
+    assert torch.equal(got[keep], padded[keep])
+    assert torch.all(got[(cols >= f[:, 4:5])[:, None, :].expand(-1, 4, -1)] == 0)
+    # a slice of it against the vectorised oracle
+    sl = slice(0, 256)
+    sub_ids = np.concatenate([ids[sl], ids[mix[sl]]])
+    x = res.padded(sub_ids).cpu().numpy()
+    fr = res.frames_of(sub_ids).numpy()
+    sub_mix = np.arange(256, 512)
+    want = orc.mix_batch_vectorised(x, fr, np.concatenate([sub_mix, np.arange(256)]), orc.lambda_as_float32(orc.draw_lambda(1.0, 2)))[:256]
+    assert np.array_equal(_bits(got[sl].cpu().numpy()), _bits(want))
