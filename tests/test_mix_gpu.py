@@ -490,3 +490,31 @@ def test_arbitrary_monotone_offsets_stress(length, seed):
     want_w = (want.astype(np.float64) * curves).astype(np.float32)
     assert int(err.item()) == 0
     assert _rel_err(out.cpu().numpy(), want_w) <= REL_TOL
+
+
+@pytest.mark.parametrize("sigma", [0.2, 0.5, 1.5])
+def test_zero_samples_keep_the_sign_the_reference_gives_them(sigma):
+    """Zero padding (and zero samples inside a cycle) times the warp factor: +0.0 where the factor is
+    positive, -0.0 where it is negative, exactly like the reference's float64 product.  With
+    sigma = 0.2 nearly every row takes the kernels' "factor certainly positive" shortcut, with
+    sigma = 1.5 many factors are negative and the shortcut must not fire."""
+    from pcgmix_b200 import synth
+    rng = np.random.default_rng(int(sigma * 10))
+    b, c, length = 96, 4, 2500
+    frames = synth.cycle_frames(rng, b, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    data[::3, :, 40:300] = 0.0                                # digital silence inside blended windows
+    data[1::3, 1, 500:508] = -0.0                             # negative zeros stay negative times a positive factor
+    labels = rng.integers(0, 2, b)
+    method = f"durmixmagwarp({sigma},4)"
+    out, _, mix, _ = _run_1d(method, 13, data, labels, frames)
+    want, want_mix, _, _ = orc.augment_1d(method, data, labels, frames, 13)
+    got = out.cpu().numpy()
+    assert np.array_equal(mix, want_mix)
+    assert _rel_err(got, want) <= REL_TOL
+    zeros = want == 0
+    assert zeros.mean() > 0.4
+    assert np.array_equal(np.signbit(got[zeros]), np.signbit(want[zeros]))
+    assert np.array_equal(got == 0, zeros)
+    if sigma >= 1.5:
+        assert np.signbit(want[zeros]).mean() > 0.02          # the case is exercised: negative factors exist
