@@ -213,12 +213,17 @@ int pcgmix_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T,
  * [B][K+2][C], coefmat, knot_pos as for pcgmix_mix1d_magwarp.  `signal` and `cycles` must be
  * 16-byte aligned.  Rows / recordings / partners out of range and offsets outside [0, L] copy the
  * cycle unmixed and raise PCGMIX_ERR_BAD_PARTNER / PCGMIX_ERR_BAD_FRAMES in *err_flag.
+ * scratch: [B][8] int32 of caller-owned device memory, 16-byte aligned, or NULL.  With scratch (and
+ * L % 4 == 0, L >= 1024, 16-byte-aligned out) a small kernel resolves the slots into records there
+ * and the persistent TMA-pipelined kernel does the work; without it a direct-load kernel is used.
+ * The result is the same.
  */
 int pcgmix_mix1d_resident(const float* signal, int32_t n_rec, int32_t C, int32_t T,
                           const int32_t* cycles, int32_t n_table, const int32_t* sel,
                           const int32_t* mix, const int32_t* order, float lam, float one_minus_lam,
                           const double* knots, const double* coefmat, const double* knot_pos, int32_t K,
-                          float* out, int32_t B, int32_t L, int32_t* err_flag, pcgmix_stream_t stream);
+                          float* out, int32_t B, int32_t L, int32_t* scratch, int32_t* err_flag,
+                          pcgmix_stream_t stream);
 
 /* 14 fp64 features per cycle from frames [n][5] int32 (stride `frame_stride` int32 between rows). */
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,

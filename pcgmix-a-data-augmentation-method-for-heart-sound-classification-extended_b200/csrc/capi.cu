@@ -133,6 +133,13 @@ void set_signature(cudaStream_t stream, unsigned long long signature, bool overl
     }
 }
 
+// A launch outside the mix bookkeeping went onto `stream`: the next mix launch there must not overlap anything.
+void forget_stream(cudaStream_t stream) {
+    std::lock_guard<std::mutex> lock(g_overlap_mutex);
+    for (int i = 0; i < g_history_used; ++i)
+        if (g_history_stream[i] == stream) g_history[i][0].valid = g_history[i][1].valid = false;
+}
+
 cudaError_t dispatch_mix(const pcgmix::MixArgs& a, bool magwarp, bool box, cudaStream_t stream) {
     const bool pipelined = g_tuning.enabled && pcgmix::pipeline_applicable(a, box);
     unsigned long long previous = 0ull;
@@ -317,7 +324,8 @@ int pcgmix_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T, cons
 int pcgmix_mix1d_resident(const float* signal, int32_t n_rec, int32_t C, int32_t T, const int32_t* cycles,
                           int32_t n_table, const int32_t* sel, const int32_t* mix, const int32_t* order, float lam,
                           float one_minus_lam, const double* knots, const double* coefmat, const double* knot_pos,
-                          int32_t K, float* out, int32_t B, int32_t L, int32_t* err_flag, pcgmix_stream_t stream) {
+                          int32_t K, float* out, int32_t B, int32_t L, int32_t* scratch, int32_t* err_flag,
+                          pcgmix_stream_t stream) {
     if (B < 0 || n_rec < 0 || n_table < 0 || C <= 0 || T < 0 || L <= 0) return fail("bad size argument");
     if (B == 0) return 0;
     if (signal == nullptr || cycles == nullptr || mix == nullptr || out == nullptr) return fail("null pointer argument");
@@ -339,7 +347,22 @@ int pcgmix_mix1d_resident(const float* signal, int32_t n_rec, int32_t C, int32_t
         a.knots = knots; a.coefmat = coefmat; a.knot_pos = knot_pos; a.K = K;
         a.inv_h = static_cast<double>(K + 1) / static_cast<double>(L - 1);
     }
-    const cudaError_t e = pcgmix::launch_mix_resident(a, magwarp, static_cast<cudaStream_t>(stream));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e;
+    if (scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0 && g_tuning.enabled &&
+        pcgmix::pipeline_applicable(a, false)) {
+        // slot records first, then the persistent TMA-pipelined kernel reading them in place of `frames`
+        e = pcgmix::launch_resolve_resident(a, scratch, st);
+        if (e == cudaSuccess) {
+            a.frames = scratch;
+            a.frame_stride = 8;
+            forget_stream(st);                                 // not part of the overlap bookkeeping of the mix launches
+            unsigned long long signature = 0ull;
+            e = pcgmix::launch_mix_pipeline(a, magwarp, g_tuning, false, 0ull, st, &signature);
+        }
+    } else {
+        e = pcgmix::launch_mix_resident(a, magwarp, st);
+    }
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_mix1d_resident", e);
 }
 

@@ -30,6 +30,17 @@
 //
 // Requirements (checked by the launcher, which otherwise uses the direct-load kernel): P % 4 == 0,
 // 16-byte-aligned tensors, P >= 1024.
+//
+// RESIDENT variant (pcgmix_mix1d_resident): the cycle's own samples are not a row of a padded
+// (B, C, L) tensor but lie somewhere inside a recording (mix_resident.cu explains the layout).  A
+// small kernel first resolves every batch slot into an 8-int record {f0..f4, first sample (64 bit),
+// samples available}; the producer reads records instead of `frames`, loads the 16-byte-aligned
+// superset of the slice's samples into a third buffer (obuf) and the partner windows from the
+// partner's recording; consumers take their samples from obuf at the slice's misalignment (two
+// aligned 128-bit shared loads and a select), zero-fill the padding and write the result to xbuf,
+// which leaves through the same bulk store.  Slices that cannot be staged (a superset would run past
+// the end of the tensor, a window reaches into the partner's padding, the windows exceed pbuf) are
+// processed sample by sample from global memory — same result.
 
 #include "common.cuh"
 
@@ -52,6 +63,11 @@ struct StageMeta {
     long long out_offset;      // element offset of the slice in x / out
     int nvec;                  // 128-bit vectors in this slice
     int t_beg;                 // first column of the slice
+    // RESIDENT only
+    const float* own_g;        // the slice's own samples in global memory (column 0 of the slice)
+    int own_n;                 // columns of the slice that hold samples (the rest is padding)
+    int own_shift;             // staged: floats between obuf[0] and column 0; -1: slice not staged (use own_g / pbase)
+    int par_n;                 // not staged: partner columns (slice-local, before the window shift) that hold samples
     alignas(16) double coef[kMaxPieces * 4];
 };
 
@@ -130,8 +146,8 @@ struct PipeArgs {
     int debug;                 // profiling only: 1 = skip stores, 2 = skip arithmetic, 4 = skip partner copies
 };
 
-template <int NCT, bool MAGWARP, int VPT>
-__global__ void __launch_bounds__(NCT + kHelperThreads, (NCT <= 192 ? 4 : NCT <= 320 ? 3 : 2))
+template <int NCT, bool MAGWARP, int VPT, bool RESIDENT>
+__global__ void __launch_bounds__(NCT + kHelperThreads, RESIDENT ? 2 : (NCT <= 192 ? 4 : NCT <= 320 ? 3 : 2))
 mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ PipeArgs pa) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);                  // loads of the stage have landed
@@ -184,7 +200,8 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     __syncthreads();
 
     auto stage_x = [&](int s) { return reinterpret_cast<float*>(stages + static_cast<size_t>(s) * pa.stage_bytes); };
-    auto stage_p = [&](int s) { return stage_x(s) + pa.slice_cap; };
+    auto stage_o = [&](int s) { return stage_x(s) + pa.slice_cap; };                      // RESIDENT: slice_cap + 8 floats
+    auto stage_p = [&](int s) { return stage_x(s) + pa.slice_cap + (RESIDENT ? pa.slice_cap + 8 : 0); };
     auto stage_meta = [&](int s) { return reinterpret_cast<StageMeta*>(stage_p(s) + pa.pbuf_cap); };
     // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const int n_it = (pa.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -241,7 +258,8 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                     wn = __ldg(w + 1);
                     f2 = f1 + __ldg(w + 2);
                 }
-            } else if (lane < 5) {
+            } else if (lane < (RESIDENT ? 8 : 5)) {
+                // RESIDENT: lanes 5..7 carry {first sample lo, hi, samples available} of the slot's record
                 f1 = __ldg(a.frames + static_cast<size_t>(b) * a.frame_stride + lane);
                 f2 = __ldg(a.frames + static_cast<size_t>(p) * a.frame_stride + lane);
             }
@@ -331,8 +349,27 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             const int w_beg = max(f1_cur, t_beg);
             const int w_end = min(f1_cur + n, t_end);
             bool have = (lane < 4) && (w_end > w_beg);
-            const int src_lo = (w_beg + d) & ~3;
-            const int src_hi = (w_end + d + 3) & ~3;
+            // RESIDENT: where this slot's and the partner's samples of this channel start inside `signal`
+            long long own_first = 0, par_first = 0;
+            int own_n = 0, par_n = 0, par_mis = 0;
+            bool stageable = true;
+            if constexpr (RESIDENT) {
+                const long long chan = static_cast<long long>(row) * a.T_sig;
+                own_first = ((static_cast<long long>(__shfl_sync(kFullMask, f1_cur, 6)) << 32) |
+                             static_cast<unsigned>(__shfl_sync(kFullMask, f1_cur, 5))) + chan;
+                par_first = ((static_cast<long long>(__shfl_sync(kFullMask, f2_cur, 6)) << 32) |
+                             static_cast<unsigned>(__shfl_sync(kFullMask, f2_cur, 5))) + chan;
+                own_n = __shfl_sync(kFullMask, f1_cur, 7);
+                par_n = __shfl_sync(kFullMask, f2_cur, 7);
+                par_mis = static_cast<int>((par_first + w_beg + d) & 3);      // misalignment of the window's first partner sample
+                // a window that reaches into the partner's padding cannot be staged (the padding is not in memory)
+                stageable = __all_sync(kFullMask, !have || w_end + d <= par_n);
+            }
+            const int src_lo = RESIDENT ? (w_beg + d - par_mis) : ((w_beg + d) & ~3);
+            const int src_hi = RESIDENT ? (src_lo + ((w_end + d - src_lo + 3) & ~3)) : ((w_end + d + 3) & ~3);
+            if constexpr (RESIDENT) {       // ... nor one whose aligned superset would run past the end of the tensor
+                stageable = __all_sync(kFullMask, stageable && !(have && par_first + src_hi > a.n_sig));
+            }
             const int cnt = have ? (src_hi - src_lo) : 0;
             int incl = cnt;
 #pragma unroll
@@ -342,7 +379,14 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
             const int off = incl - cnt;
             int total = __shfl_sync(kFullMask, incl, 3);
-            const bool staged = total <= pa.pbuf_cap && !(pa.debug & 4);   // else: consumers read the partner from global memory
+            // the slice's own samples (RESIDENT): aligned superset [own_lo, own_lo + own_cnt) of the tensor
+            const int own_local = RESIDENT ? min(max(own_n - t_beg, 0), t_end - t_beg) : 0;
+            const int own_shift = RESIDENT ? static_cast<int>((own_first + t_beg) & 3) : 0;
+            const int own_cnt = own_local > 0 ? ((own_shift + own_local + 3) & ~3) : 0;
+            if constexpr (RESIDENT) {
+                if (own_first + t_beg - own_shift + own_cnt > a.n_sig) stageable = false;
+            }
+            const bool staged = total <= pa.pbuf_cap && !(pa.debug & 4) && stageable;   // else: consumers read from global memory
             if (!staged) {
                 have = false;
                 total = 0;
@@ -355,14 +399,21 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             float* pbuf = stage_p(stage);
             StageMeta* meta = stage_meta(stage);
             const long long row_off = (static_cast<long long>(b) * a.R + row) * a.P;
-            const long long prow = (static_cast<long long>(p) * a.R + row) * a.P;
+            const long long prow = RESIDENT ? par_first : (static_cast<long long>(p) * a.R + row) * a.P;
+            const float* src_base = RESIDENT ? a.signal : a.x;
             if (lane < 4) {
                 const int next = (lane < 3) ? f1n : a.P;
                 const int shift = staged ? (t_beg + d - src_lo + off) : d;
                 meta->win[lane] = make_int4(f1_cur - t_beg, n, shift, next - t_beg);
             }
             if (lane == 0) {
-                meta->pbase = staged ? pbuf : (a.x + prow + t_beg);
+                meta->pbase = staged ? pbuf : (src_base + prow + t_beg);
+                if constexpr (RESIDENT) {
+                    meta->own_g = a.signal + own_first + t_beg;
+                    meta->own_n = own_local;
+                    meta->own_shift = staged ? own_shift : -1;
+                    meta->par_n = par_n - t_beg;
+                }
                 meta->out_offset = row_off + t_beg;
                 meta->nvec = (t_end - t_beg) >> 2;
                 meta->t_beg = t_beg;
@@ -377,11 +428,21 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 if (lane + 96 < n_coef) meta->coef[lane + 96] = acc3;
             }
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>((t_end - t_beg) + total) * 4u);
-                bulk_load(xbuf, a.x + row_off + t_beg, static_cast<uint32_t>(t_end - t_beg) * 4u, &full[stage]);
+            if constexpr (RESIDENT) {
+                const int own_load = staged ? own_cnt : 0;
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(own_load + total) * 4u);
+                    if (own_load > 0)
+                        bulk_load(stage_o(stage), a.signal + (own_first + t_beg - own_shift), static_cast<uint32_t>(own_load) * 4u, &full[stage]);
+                }
+                if (have) bulk_load(pbuf + off, a.signal + prow + src_lo, static_cast<uint32_t>(cnt) * 4u, &full[stage]);
+            } else {
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>((t_end - t_beg) + total) * 4u);
+                    bulk_load(xbuf, a.x + row_off + t_beg, static_cast<uint32_t>(t_end - t_beg) * 4u, &full[stage]);
+                }
+                if (have) bulk_load(pbuf + off, a.x + prow + src_lo, static_cast<uint32_t>(cnt) * 4u, &full[stage]);
             }
-            if (have) bulk_load(pbuf + off, a.x + prow + src_lo, static_cast<uint32_t>(cnt) * 4u, &full[stage]);
             stage += NP;                                   // NP <= S is guaranteed by the launcher
             if (stage >= S) {
                 stage -= S;
@@ -435,17 +496,60 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             const int nvec = meta->nvec;
             const int t_beg = meta->t_beg;
             const float* pbase = meta->pbase;
+            const float* obuf = stage_o(stage);
+            const float* own_g = RESIDENT ? meta->own_g : nullptr;
+            const int own_n = RESIDENT ? meta->own_n : 0;
+            const int own_shift = RESIDENT ? meta->own_shift : 0;
+            const int par_n = RESIDENT ? meta->par_n : 0;
 #pragma unroll
             for (int k = 0; k < VPT; ++k) {
                 const int v = ct + k * NCT;
                 if (v < nvec && !(pa.debug & 2)) {
                     const int col = v * 4;                                   // local column
-                    const float4 mine = *reinterpret_cast<const float4*>(xbuf + col);
-                    float r[4] = {mine.x, mine.y, mine.z, mine.w};
+                    float r[4];
+                    if constexpr (RESIDENT) {
+                        if (__builtin_expect(own_shift < 0, 0)) {            // slice not staged: sample by sample from global memory
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int t = col + e;
+                                r[e] = t < own_n ? __ldg(own_g + t) : 0.0f;
+                                const int se = (t >= lo1) + (t >= lo2) + (t >= lo3);
+                                const int4 we = meta->win[se];
+                                if (static_cast<unsigned>(t - we.x) < static_cast<unsigned>(we.y)) {
+                                    const float o = t + we.z < par_n ? __ldg(pbase + t + we.z) : 0.0f;
+                                    r[e] = __fadd_rn(__fmul_rn(r[e], a.lam), __fmul_rn(o, a.one_minus_lam));
+                                }
+                            }
+                        } else {
+                            r[0] = r[1] = r[2] = r[3] = 0.0f;
+                            if (col < own_n) {
+                                const float4 lo = *reinterpret_cast<const float4*>(obuf + col);
+                                const float4 hi = *reinterpret_cast<const float4*>(obuf + col + 4);
+                                if (own_shift == 0) {                        // uniform over the item
+                                    r[0] = lo.x; r[1] = lo.y; r[2] = lo.z; r[3] = lo.w;
+                                } else if (own_shift == 1) {
+                                    r[0] = lo.y; r[1] = lo.z; r[2] = lo.w; r[3] = hi.x;
+                                } else if (own_shift == 2) {
+                                    r[0] = lo.z; r[1] = lo.w; r[2] = hi.x; r[3] = hi.y;
+                                } else {
+                                    r[0] = lo.w; r[1] = hi.x; r[2] = hi.y; r[3] = hi.z;
+                                }
+                                if (col + 4 > own_n) {                       // the vector holding the cycle's last sample
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) r[e] = col + e < own_n ? r[e] : 0.0f;
+                                }
+                            }
+                        }
+                    } else {
+                        const float4 mine = *reinterpret_cast<const float4*>(xbuf + col);
+                        r[0] = mine.x; r[1] = mine.y; r[2] = mine.z; r[3] = mine.w;
+                    }
                     const int s = (col >= lo1) + (col >= lo2) + (col >= lo3);
                     const int4 w = meta->win[s];
                     const int ahead = col - w.x;
-                    if (__builtin_expect(ahead >= 0 && col + 3 < w.w, 1)) {
+                    if (RESIDENT && own_shift < 0) {
+                        // blended above
+                    } else if (__builtin_expect(ahead >= 0 && col + 3 < w.w, 1)) {
                         const int m = w.y - ahead;                           // leading samples that blend
                         if (m > 0) {
                             const float* src = pbase + col + w.z;
@@ -512,15 +616,15 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     }
 }
 
-template <int NCT, int VPT>
+template <int NCT, int VPT, bool RESIDENT>
 cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, int grid, size_t smem, bool magwarp, bool overlap_previous,
                        cudaStream_t stream) {
     // opt in to the large dynamic shared-memory carve-out once per kernel instance
     static bool allowed[2] = {false, false};
     if (!allowed[magwarp ? 1 : 0]) {
         const cudaError_t e = magwarp
-            ? cudaFuncSetAttribute(mix_pipeline_kernel<NCT, true, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-            : cudaFuncSetAttribute(mix_pipeline_kernel<NCT, false, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            ? cudaFuncSetAttribute(mix_pipeline_kernel<NCT, true, VPT, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
+            : cudaFuncSetAttribute(mix_pipeline_kernel<NCT, false, VPT, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         allowed[magwarp ? 1 : 0] = true;
     }
@@ -534,8 +638,8 @@ cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, int grid, size_t sm
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = overlap_previous ? 1 : 0;
-    return magwarp ? cudaLaunchKernelEx(&cfg, mix_pipeline_kernel<NCT, true, VPT>, a, pa)
-                   : cudaLaunchKernelEx(&cfg, mix_pipeline_kernel<NCT, false, VPT>, a, pa);
+    return magwarp ? cudaLaunchKernelEx(&cfg, mix_pipeline_kernel<NCT, true, VPT, RESIDENT>, a, pa)
+                   : cudaLaunchKernelEx(&cfg, mix_pipeline_kernel<NCT, false, VPT, RESIDENT>, a, pa);
 }
 
 int g_sm_count = 0;
@@ -543,7 +647,8 @@ int g_sm_count = 0;
 }  // namespace
 
 bool pipeline_applicable(const MixArgs& a, bool box) {
-    const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out)) & 15u) == 0;
+    const void* src = a.signal != nullptr ? static_cast<const void*>(a.signal) : static_cast<const void*>(a.x);
+    const bool aligned16 = ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(a.out)) & 15u) == 0;
     return !box && aligned16 && (a.P % 4) == 0 && a.P >= 1024;
 }
 
@@ -552,6 +657,8 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
                                 unsigned long long* full_grid_signature) {
     MixArgs a = base;
     a.n_per_cycle = a.R * a.P;
+    const bool resident = a.signal != nullptr;               // records in a.frames (stride 8), samples in a.signal
+    if (resident) a.n_sig = static_cast<long long>(a.n_rec) * a.R * a.T_sig;
     if (magwarp) {
         const double ratio = static_cast<double>(a.K + 1) / static_cast<double>(a.P - 1);
         const double scaled = ratio * 4294967296.0 * (1.0 - 1e-9);
@@ -579,7 +686,7 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     if (pa.stages < kProducerWarps) pa.stages = kProducerWarps;
     // only the (K+1)*4 coefficients in use are reserved at the end of the metadata block
     const size_t meta_bytes = sizeof(StageMeta) - sizeof(double) * (kMaxPieces * 4 - (magwarp ? (a.K + 1) * 4 : 0));
-    const size_t stage_bytes = (static_cast<size_t>(pa.slice_cap) + pa.pbuf_cap) * sizeof(float) + meta_bytes;
+    const size_t stage_bytes = (static_cast<size_t>(pa.slice_cap) * (resident ? 2 : 1) + (resident ? 8 : 0) + pa.pbuf_cap) * sizeof(float) + meta_bytes;
     pa.stage_bytes = static_cast<int>((stage_bytes + 127) & ~static_cast<size_t>(127));
     const size_t mat_bytes = magwarp ? static_cast<size_t>(a.K + 1) * 4 * (a.K + 2) * sizeof(double) : 0;
     pa.header_bytes = static_cast<int>((kHeaderBytes + mat_bytes + 127) & ~static_cast<size_t>(127));
@@ -589,7 +696,7 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     if (n_items > 2147483647LL) return cudaErrorInvalidConfiguration;
     pa.n_items = static_cast<int>(n_items);
     pa.debug = tune.debug;
-    const int vpt = tune.vec_per_thread == 1 ? 1 : 2;
+    const int vpt = (tune.vec_per_thread == 1 && !resident) ? 1 : 2;
     const int need = ((slice_len / 4) + vpt - 1) / vpt;                       // consumer threads with work
     if (need > 448) return cudaErrorInvalidConfiguration;
     int nct = need <= 128 ? 128 : need <= 192 ? 192 : need <= 256 ? 256 : need <= 320 ? 320 : need <= 384 ? 384 : 448;
@@ -617,23 +724,34 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     pa.stepn_rest = static_cast<int>((grid * kProducerWarps) / a.B);
     pa.stepn_slot = static_cast<int>((grid * kProducerWarps) % a.B);
     if (pa.stages < kProducerWarps) return cudaErrorInvalidConfiguration;
+    const int g = static_cast<int>(grid);
+    if (resident) {
+        switch (nct) {
+            case 128: return launch_nct<128, 2, true>(a, pa, g, smem, magwarp, false, stream);
+            case 192: return launch_nct<192, 2, true>(a, pa, g, smem, magwarp, false, stream);
+            case 256: return launch_nct<256, 2, true>(a, pa, g, smem, magwarp, false, stream);
+            case 320: return launch_nct<320, 2, true>(a, pa, g, smem, magwarp, false, stream);
+            case 384: return launch_nct<384, 2, true>(a, pa, g, smem, magwarp, false, stream);
+            default: return launch_nct<448, 2, true>(a, pa, g, smem, magwarp, false, stream);
+        }
+    }
     if (vpt == 1) {
         switch (nct) {
-            case 128: return launch_nct<128, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-            case 192: return launch_nct<192, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-            case 256: return launch_nct<256, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-            case 320: return launch_nct<320, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-            case 384: return launch_nct<384, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-            default: return launch_nct<448, 1>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+            case 128: return launch_nct<128, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+            case 192: return launch_nct<192, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+            case 256: return launch_nct<256, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+            case 320: return launch_nct<320, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+            case 384: return launch_nct<384, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+            default: return launch_nct<448, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
         }
     }
     switch (nct) {
-        case 128: return launch_nct<128, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-        case 192: return launch_nct<192, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-        case 256: return launch_nct<256, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-        case 320: return launch_nct<320, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-        case 384: return launch_nct<384, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
-        default: return launch_nct<448, 2>(a, pa, static_cast<int>(grid), smem, magwarp, overlap_previous, stream);
+        case 128: return launch_nct<128, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+        case 192: return launch_nct<192, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+        case 256: return launch_nct<256, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+        case 320: return launch_nct<320, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+        case 384: return launch_nct<384, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+        default: return launch_nct<448, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
     }
 }
 

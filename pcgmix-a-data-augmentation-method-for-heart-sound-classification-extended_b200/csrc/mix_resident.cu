@@ -307,7 +307,40 @@ cudaError_t launch_t(const MixArgs& a, dim3 grid, bool magwarp, cudaStream_t str
     return cudaGetLastError();
 }
 
+// One thread per batch slot: the slot's table row resolved into the 8-int record the pipelined
+// kernel reads instead of `frames`: {f0..f4, first sample of channel 0 (64-bit element index, lo/hi),
+// samples available}.  A slot whose table row or recording does not exist gets an empty record (all
+// padding, nothing blended) and raises PCGMIX_ERR_BAD_PARTNER.
+__global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ MixArgs a, int32_t* __restrict__ records) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const int table_row = a.sel ? __ldg(a.sel + b) : b;
+    int4 lo = make_int4(0, 0, 0, 0), hi = make_int4(0, 0, 0, 0);
+    bool ok = static_cast<unsigned>(table_row) < static_cast<unsigned>(a.n_table);
+    if (ok) {
+        const int4 head = __ldg(reinterpret_cast<const int4*>(a.cycles) + static_cast<size_t>(table_row) * 2);
+        const int4 tail = __ldg(reinterpret_cast<const int4*>(a.cycles) + static_cast<size_t>(table_row) * 2 + 1);
+        ok = static_cast<unsigned>(head.x) < static_cast<unsigned>(a.n_rec);
+        if (ok) {
+            const int start = min(max(head.y, 0), a.T_sig);
+            const int stop = min(max(head.z, start), a.T_sig);
+            const long long first = static_cast<long long>(head.x) * a.R * a.T_sig + start;
+            lo = make_int4(head.w, tail.x, tail.y, tail.z);
+            hi = make_int4(tail.w, static_cast<int>(first & 0xffffffffLL), static_cast<int>(first >> 32), min(stop - start, a.P));
+        }
+    }
+    reinterpret_cast<int4*>(records)[static_cast<size_t>(b) * 2] = lo;
+    reinterpret_cast<int4*>(records)[static_cast<size_t>(b) * 2 + 1] = hi;
+    if (!ok && a.err != nullptr) atomicOr(a.err, static_cast<int>(PCGMIX_ERR_BAD_PARTNER));
+}
+
 }  // namespace
+
+cudaError_t launch_resolve_resident(const MixArgs& a, int32_t* records, cudaStream_t stream) {
+    if (a.B == 0) return cudaSuccess;
+    resolve_kernel<<<(a.B + 255) / 256, 256, 0, stream>>>(a, records);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_mix_resident(const MixArgs& base, bool magwarp, cudaStream_t stream) {
     MixArgs a = base;

@@ -49,7 +49,7 @@ SIGNATURES = {
     "pcgmix_cut_cycles": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _c_i32, _ptr],
     "pcgmix_duration_features": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_mix1d_resident": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr, _c_f32, _c_f32,
-                              _ptr, _ptr, _ptr, _c_i32, _ptr, _c_i32, _c_i32, _ptr, _ptr],
+                              _ptr, _ptr, _ptr, _c_i32, _ptr, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_copy_small": [_ptr, _ptr, ctypes.c_int64, _ptr],
     "pcgmix_host_group_permutation": [_ptr, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, _ptr],
 }
@@ -396,9 +396,10 @@ def cut_cycles(signal, cycles, n_cycles, out, n_cycles_dev=None):
 
 
 def mix1d_resident(signal, cycles, sel, mix, lam32, one_minus_lam32, out, knots=None, coefmat=None, knot_pos=None,
-                   knot=0, order=None, err_flag=None):
+                   knot=0, order=None, err_flag=None, scratch=None):
     """Cut + zero-pad + PCGmix(+) in one launch: ``signal`` (n_rec, C, T) fp32, ``cycles`` (n_table, 8) int32
-    cycle table, ``sel`` (B,) int32 table rows of the batch or None, ``out`` (B, C, L)."""
+    cycle table, ``sel`` (B,) int32 table rows of the batch or None, ``out`` (B, C, L); ``scratch`` (B, 8) int32
+    lets the library use the pipelined kernel (slot records are written there first)."""
     global launch_count
     n_rec, C, T = signal.shape
     B, C_out, L = out.shape
@@ -406,7 +407,9 @@ def mix1d_resident(signal, cycles, sel, mix, lam32, one_minus_lam32, out, knots=
         raise ValueError(f"out has {C_out} channels, the recordings have {C}")
     if cycles.dim() != 2 or cycles.shape[1] != 8 or not cycles.is_contiguous():
         raise ValueError("cycles must be a contiguous (n, 8) int32 cycle table")
-    dev = _same_device(signal, cycles, sel, mix, out, knots, coefmat, knot_pos, order, err_flag)
+    dev = _same_device(signal, cycles, sel, mix, out, knots, coefmat, knot_pos, order, err_flag, scratch)
+    if scratch is not None and (scratch.numel() < 8 * B or not scratch.is_contiguous()):
+        raise ValueError("scratch must be a contiguous int32 tensor of at least B*8 elements")
     with _on_device(dev):
         rc = load().pcgmix_mix1d_resident(
             _dev_ptr(signal, torch.float32, "signal"), n_rec, C, T, _dev_ptr(cycles, torch.int32, "cycles"),
@@ -414,10 +417,10 @@ def mix1d_resident(signal, cycles, sel, mix, lam32, one_minus_lam32, out, knots=
             _dev_ptr(order, torch.int32, "order", True), float(lam32), float(one_minus_lam32),
             _dev_ptr(knots, torch.float64, "knots", True), _dev_ptr(coefmat, torch.float64, "coefmat", True),
             _dev_ptr(knot_pos, torch.float64, "knot_pos", True), int(knot),
-            _dev_ptr(out, torch.float32, "out"), B, L, _dev_ptr(err_flag, torch.int32, "err_flag", True),
-            _stream_handle(dev))
+            _dev_ptr(out, torch.float32, "out"), B, L, _dev_ptr(scratch, torch.int32, "scratch", True),
+            _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
     _check(rc, "pcgmix_mix1d_resident")
-    launch_count += 1 if B > 0 else 0
+    launch_count += (2 if scratch is not None else 1) if B > 0 else 0
 
 
 def duration_features(frames, n, fs, features, err_flag=None):

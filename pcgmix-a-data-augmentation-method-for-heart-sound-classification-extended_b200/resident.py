@@ -101,10 +101,13 @@ def from_state_table(signal: torch.Tensor, positions, codes, rec_offsets, length
 
 
 def mix_rows(resident: ResidentCycles, sel_dev, mix_dev, lam32, one_minus_lam32, knots_dev=None, knot=0,
-             order_dev=None, out=None) -> torch.Tensor:
-    """Device-resident entry: one launch, everything already on the GPU (``sel_dev`` may be None for
-    "rows 0..B-1", then ``out`` or ``mix_dev`` gives B)."""
+             order_dev=None, out=None, scratch=None) -> torch.Tensor:
+    """Device-resident entry, everything already on the GPU (``sel_dev`` may be None for "rows 0..B-1").
+    ``scratch``: (B, 8) int32 work space for the slot records of the pipelined kernel; allocated from
+    PyTorch's caching allocator when not given."""
     batch = mix_dev.shape[0]
+    if scratch is None:
+        scratch = torch.empty((batch, 8), dtype=torch.int32, device=resident.signal.device)
     if out is None:
         out = torch.empty((batch, resident.channels, resident.length), dtype=torch.float32, device=resident.signal.device)
     pos_dev = mat_dev = None
@@ -113,7 +116,7 @@ def mix_rows(resident: ResidentCycles, sel_dev, mix_dev, lam32, one_minus_lam32,
             raise ValueError(f"durmixmagwarp knot={knot} exceeds the supported maximum {native.MAX_KNOT}")
         pos_dev, mat_dev = _device_tables(resident.length, knot, resident.signal.device)
     native.mix1d_resident(resident.signal, resident.table.cycles, sel_dev, mix_dev, lam32, one_minus_lam32, out,
-                          knots_dev, mat_dev, pos_dev, knot, order=order_dev, err_flag=resident.err_flag)
+                          knots_dev, mat_dev, pos_dev, knot, order=order_dev, err_flag=resident.err_flag, scratch=scratch)
     return out
 
 

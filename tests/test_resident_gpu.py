@@ -14,6 +14,16 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5       # north_star: float outputs within 1e-5 relative of the NumPy reference
 
 
+@pytest.fixture(autouse=True, params=["pipeline", "direct"])
+def kernel_choice(request):
+    """Every test runs twice: slot records + the persistent TMA-pipelined kernel (rows of >= 1024
+    samples, L % 4 == 0), and with the pipelined kernels switched off (direct-load kernel)."""
+    from pcgmix_b200 import native
+    native.set_tuning(use_pipeline=request.param == "pipeline")
+    yield request.param
+    native.set_tuning(use_pipeline=True)
+
+
 class _Args:
     def __init__(self, method, batch):
         self.method, self.batch_size, self.sample_rate, self.num_classes = method, batch, 1000, 2
@@ -131,7 +141,7 @@ def test_cycles_touching_the_end_of_the_tensor_and_too_long_cycles(warp):
     than L (offsets outside [0, L]: copied unmixed and flagged, like the two-step path)."""
     from pcgmix_b200 import draws, resident
     rng = np.random.default_rng(3)
-    t_len, length = 3001, 1000
+    t_len, length = 3001, 1200
     signal = rng.standard_normal((2, 1, t_len)).astype(np.float32)              # 6002 floats
     rows = [
         [1, 2301, 3001, 0, 100, 300, 400, 700],      # ends at the very last element of the tensor
@@ -158,9 +168,9 @@ def test_out_of_range_rows_and_partners_are_flagged_not_followed():
     rng = np.random.default_rng(4)
     signal = rng.standard_normal((1, 2, 4000)).astype(np.float32)
     rows = [[0, 0, 900, 0, 100, 400, 500, 900], [0, 1000, 1800, 0, 90, 300, 420, 800], [7, 0, 900, 0, 100, 400, 500, 900]]
-    res = _hand_made(signal, rows, 1000)
+    res = _hand_made(signal, rows, 1024)
     lam = draws.lambda_pair_fp32(0.5)
-    guard = torch.full((6, 2, 1000), 7.0, device="cuda")
+    guard = torch.full((6, 2, 1024), 7.0, device="cuda")
     out = guard[1:5]
     sel = torch.tensor([0, 5, 2, 1], dtype=torch.int32, device="cuda")          # row 5 does not exist; row 2 names recording 7
     mix = torch.tensor([3, 0, 0, 9], dtype=torch.int32, device="cuda")          # partner 9 does not exist
