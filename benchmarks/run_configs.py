@@ -106,6 +106,8 @@ def resident_section(args, dev):
         emit("resident/%s fused cut+pad+mix from %d recordings x %d x %d, batch %d x %d" % (name, n_rec, C, Tr, Br, L),
              Br, ms, mn, 4.0 * C * (own + mm + L * Br),
              note="bytes = 4*C*(sum len1 + sum M + B*L); mean cycle %.0f samples of L=%d" % (own / Br, L))
+        if args.only == "resident" and (args.stages or args.ctas_per_sm or args.consumer_threads or args.max_slice or args.pbuf_pct):
+            continue
         ms2, mn2 = timed(two_step, 50)
         emit("resident/%s two-step: row gather + cut_cycles + mix kernel (what the fused kernel replaces)" % name,
              Br, ms2, mn2, note="fused is %.2fx faster" % (ms2 / ms))
@@ -116,9 +118,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=200)
     ap.add_argument("--only", default="", choices=["", "resident"])
+    ap.add_argument("--stages", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", type=int, default=0)
+    ap.add_argument("--consumer-threads", type=int, default=0)
+    ap.add_argument("--max-slice", type=int, default=0)
+    ap.add_argument("--pbuf-pct", type=int, default=0)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     native.load()
+    native.set_tuning(True, args.stages, args.max_slice, args.ctas_per_sm, args.pbuf_pct, args.consumer_threads, 0)
     if args.only == "resident":
         return resident_section(args, dev)
     rng = np.random.default_rng(synth.BENCH_SEED)

@@ -131,7 +131,12 @@ int pcgmix_mix1d(const float* x, float* out, const int32_t* frames, int32_t fram
  *   knots ........ [B][K+2][C] fp64, the reference's N(1,sigma) draw, in the drawn layout
  *   coefmat ...... [(K+1)*4][K+2] fp64: linear map knots -> piecewise-cubic coefficients of
  *                  the not-a-knot spline, row (k*4+i) = coefficient of dt^(3-i) on piece k
- *   knot_pos ..... [K+2] fp64: np.linspace(0, L-1, K+2)
+ *   knot_pos ..... [K+3] fp64: np.linspace(0, L-1, K+2), followed by ONE more value d >= 0: a bound
+ *                  such that max_j |knot_j - 1| < d guarantees spline(t) > 0 at every sample
+ *                  (0.999 / Lebesgue constant of the knot -> curve map; 0 = not known).  Used by
+ *                  pcgmix_mix1d_resident, which knows which samples are zero padding: for rows
+ *                  inside the bound padding is written as +0.0f without evaluating the spline
+ *                  ((+0.0f) * w is +0.0f for every positive finite w)
  * out = fp32( fp64(mixed) * spline(t) ), like the reference's float64 product stored to fp32.
  */
 int pcgmix_mix1d_magwarp(const float* x, float* out, const int32_t* frames, int32_t frame_stride,

@@ -68,6 +68,7 @@ struct StageMeta {
     int own_n;                 // columns of the slice that hold samples (the rest is padding)
     int own_shift;             // staged: floats between obuf[0] and column 0; -1: slice not staged (use own_g / pbase)
     int par_n;                 // not staged: partner columns (slice-local, before the window shift) that hold samples
+    int positive;              // 1: the row's warp factor is certainly > 0 and finite at every sample
     alignas(16) double coef[kMaxPieces * 4];
 };
 
@@ -268,6 +269,14 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         double y0 = 0.0;
         bool bad0 = false;
         constexpr int NP = kProducerWarps;
+        // RESIDENT: knot_pos[K+2] is the largest knot deviation from 1 that keeps the warp factor positive
+        // (spline.safe_deviation; 0 disables the shortcut).  Rounded DOWN to fp32 and compared as bit patterns
+        // (non-negative floats order like unsigned integers; NaN orders above every bound).
+        unsigned safe_dev_bits = 0u;
+        if constexpr (RESIDENT && MAGWARP) safe_dev_bits = __float_as_uint(__double2float_rd(fmax(__ldg(a.knot_pos + a.K + 2), 0.0)));
+        // RESIDENT: the slot records are written by the kernel launched just before this one; everything
+        // above (barriers, knot tables, coefficient matrix) did not need them
+        if constexpr (RESIDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
         Cursor c0{static_cast<int>(blockIdx.x % a.B), static_cast<int>(blockIdx.x / a.B)};   // item it
         for (int k = 0; k < pw; ++k) c0 = advance1(c0);
         Cursor c1 = advance(c0), c2 = advance(c1), c3 = advance(c2);                          // this warp's next three
@@ -330,6 +339,14 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                         if (lane + 96 < n_coef) acc3 = fma(mrow[96 * n_knots + j], yj, acc3);
                     }
                 }
+            }
+            // The curve reproduces constants and is linear in the knots: |w(t) - 1| <= Lambda * max_j |y_j - 1|.
+            // Rows inside the bound have a positive, finite factor everywhere; consumers then write padding
+            // (exact +0.0f) without evaluating the spline.
+            int row_positive = 0;
+            if constexpr (RESIDENT && MAGWARP) {
+                const float dev = lane < a.K + 2 ? fabsf(static_cast<float>(y_cur) - 1.0f) : 0.0f;
+                row_positive = __reduce_max_sync(kFullMask, __float_as_uint(dev)) < safe_dev_bits ? 1 : 0;
             }
             const int f1n = __shfl_down_sync(kFullMask, f1_cur, 1);
             const int f2n = __shfl_down_sync(kFullMask, f2_cur, 1);
@@ -409,6 +426,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             if (lane == 0) {
                 meta->pbase = staged ? pbuf : (src_base + prow + t_beg);
                 if constexpr (RESIDENT) {
+                    meta->positive = row_positive;
                     meta->own_g = a.signal + own_first + t_beg;
                     meta->own_n = own_local;
                     meta->own_shift = staged ? own_shift : -1;
@@ -501,6 +519,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             const int own_n = RESIDENT ? meta->own_n : 0;
             const int own_shift = RESIDENT ? meta->own_shift : 0;
             const int par_n = RESIDENT ? meta->par_n : 0;
+            const bool positive = RESIDENT && MAGWARP && meta->positive != 0;
 #pragma unroll
             for (int k = 0; k < VPT; ++k) {
                 const int v = ct + k * NCT;
@@ -547,11 +566,14 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                     const int s = (col >= lo1) + (col >= lo2) + (col >= lo3);
                     const int4 w = meta->win[s];
                     const int ahead = col - w.x;
+                    // padding that no window touches: +0.0f, and +0.0f times a positive finite factor is +0.0f
+                    bool padding = RESIDENT && MAGWARP && positive && own_shift >= 0 && col >= own_n;
                     if (RESIDENT && own_shift < 0) {
                         // blended above
                     } else if (__builtin_expect(ahead >= 0 && col + 3 < w.w, 1)) {
                         const int m = w.y - ahead;                           // leading samples that blend
                         if (m > 0) {
+                            padding = false;
                             const float* src = pbase + col + w.z;
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
@@ -559,6 +581,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                             }
                         }
                     } else {
+                        padding = false;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
                             const int t = col + e;
@@ -567,6 +590,10 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                             if (static_cast<unsigned>(t - we.x) < static_cast<unsigned>(we.y))
                                 r[e] = __fadd_rn(__fmul_rn(r[e], a.lam), __fmul_rn(pbase[t + we.z], a.one_minus_lam));
                         }
+                    }
+                    if (RESIDENT && MAGWARP && padding) {
+                        *reinterpret_cast<float4*>(xbuf + col) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                        continue;
                     }
                     if constexpr (MAGWARP) {
                         const int t = t_beg + col;
@@ -726,13 +753,15 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     if (pa.stages < kProducerWarps) return cudaErrorInvalidConfiguration;
     const int g = static_cast<int>(grid);
     if (resident) {
+        // launched with the programmatic attribute: the kernel right before it on the stream is the slot-record
+        // kernel, which lets it start early; the producers wait for the records (griddepcontrol.wait)
         switch (nct) {
-            case 128: return launch_nct<128, 2, true>(a, pa, g, smem, magwarp, false, stream);
-            case 192: return launch_nct<192, 2, true>(a, pa, g, smem, magwarp, false, stream);
-            case 256: return launch_nct<256, 2, true>(a, pa, g, smem, magwarp, false, stream);
-            case 320: return launch_nct<320, 2, true>(a, pa, g, smem, magwarp, false, stream);
-            case 384: return launch_nct<384, 2, true>(a, pa, g, smem, magwarp, false, stream);
-            default: return launch_nct<448, 2, true>(a, pa, g, smem, magwarp, false, stream);
+            case 128: return launch_nct<128, 2, true>(a, pa, g, smem, magwarp, true, stream);
+            case 192: return launch_nct<192, 2, true>(a, pa, g, smem, magwarp, true, stream);
+            case 256: return launch_nct<256, 2, true>(a, pa, g, smem, magwarp, true, stream);
+            case 320: return launch_nct<320, 2, true>(a, pa, g, smem, magwarp, true, stream);
+            case 384: return launch_nct<384, 2, true>(a, pa, g, smem, magwarp, true, stream);
+            default: return launch_nct<448, 2, true>(a, pa, g, smem, magwarp, true, stream);
         }
     }
     if (vpt == 1) {

@@ -312,6 +312,9 @@ cudaError_t launch_t(const MixArgs& a, dim3 grid, bool magwarp, cudaStream_t str
 // samples available}.  A slot whose table row or recording does not exist gets an empty record (all
 // padding, nothing blended) and raises PCGMIX_ERR_BAD_PARTNER.
 __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ MixArgs a, int32_t* __restrict__ records) {
+    // the pipelined kernel behind us may start its prologue now; it waits (griddepcontrol.wait) for this
+    // grid to finish before it reads a record
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
     const int table_row = a.sel ? __ldg(a.sel + b) : b;

@@ -253,7 +253,7 @@ def mix1d_magwarp(x, out, frames, mix, lam32, one_minus_lam32, knots, coefmat, k
     B, C, L = x.shape
     if tuple(knots.shape) != (B, knot + 2, C):
         raise ValueError(f"knots must be (B, knot+2, C) = {(B, knot + 2, C)}, got {tuple(knots.shape)}")
-    if tuple(coefmat.shape) != ((knot + 1) * 4, knot + 2) or tuple(knot_pos.shape) != (knot + 2,):
+    if tuple(coefmat.shape) != ((knot + 1) * 4, knot + 2) or tuple(knot_pos.shape) != (knot + 3,):
         raise ValueError("coefmat / knot_pos do not match knot")
     dev = _same_device(x, out, frames, mix, order, err_flag, knots, coefmat, knot_pos)
     fptr, fstride = _frames_ptr(frames)

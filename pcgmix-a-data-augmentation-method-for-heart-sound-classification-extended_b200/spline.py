@@ -90,17 +90,43 @@ def coefficient_matrix_for(x: np.ndarray) -> np.ndarray:
     return M
 
 
+def _curves(coef_rows: np.ndarray, x: np.ndarray, n_samples: int) -> np.ndarray:
+    t = np.arange(n_samples, dtype=np.float64)
+    piece = np.clip(np.searchsorted(x, t, side="right") - 1, 0, x.shape[0] - 2)
+    dt = t - x[piece]
+    c = coef_rows.reshape(coef_rows.shape[:-1] + (x.shape[0] - 1, 4))[..., piece, :]
+    return ((c[..., 0] * dt + c[..., 1]) * dt + c[..., 2]) * dt + c[..., 3]
+
+
+def safe_deviation(x: np.ndarray, M: np.ndarray, n_samples: int) -> float:
+    """Largest ``max_j |y_j - 1|`` for which the warp curve is certainly positive at every sample.
+
+    The curve is linear in the ordinates and reproduces constants, so at sample ``t`` it equals
+    ``1 + sum_j l_j(t) (y_j - 1)`` with ``l_j`` the curve through the j-th unit vector; hence
+    ``|w(t) - 1| <= Lambda * max_j |y_j - 1|`` with ``Lambda = max_t sum_j |l_j(t)|`` taken over
+    the samples actually evaluated (1.94 for knot = 4).  Below ``0.999 / Lambda`` every factor is
+    ``> 1e-3``: exact zeros (the padding after a cycle) times the factor are ``+0.0`` and a kernel
+    that knows which samples are padding may leave them alone.  With sigma = 0.2 about 94 % of all
+    (cycle, channel) rows qualify."""
+    basis = _curves(M.T.copy(), x, n_samples)                  # (n, L): row j = l_j at every sample
+    lebesgue = float(np.abs(basis).sum(axis=0).max())
+    return 0.999 / lebesgue if np.isfinite(lebesgue) and lebesgue > 0 else 0.0
+
+
 @functools.lru_cache(maxsize=64)
 def _cached(n_samples: int, knot: int):
     x = knot_positions(n_samples, knot)
     M = coefficient_matrix_for(x)
-    x.setflags(write=False)
+    pos = np.concatenate([x, [safe_deviation(x, M, n_samples)]])
+    pos.setflags(write=False)
     M.setflags(write=False)
-    return x, M
+    return pos, M
 
 
 def magwarp_tables(n_samples: int, knot: int):
-    """``(knot_pos (knot+2,), coefmat ((knot+1)*4, knot+2))`` float64, cached per ``(L, knot)``."""
+    """``(knot_pos (knot+3,), coefmat ((knot+1)*4, knot+2))`` float64, cached per ``(L, knot)``.
+    ``knot_pos[:knot+2]`` are the abscissae, ``knot_pos[knot+2]`` is :func:`safe_deviation` — the
+    layout ``include/pcgmix_b200.h`` asks for."""
     if knot < 0:
         raise ValueError("knot must be >= 0")
     return _cached(int(n_samples), int(knot))
@@ -110,10 +136,5 @@ def evaluate(knots: np.ndarray, n_samples: int) -> np.ndarray:
     """Host evaluation of the warp curves through ``M`` — used by tests to compare the linear-map
     formulation with SciPy; ``knots`` (..., knot+2) -> (..., L)."""
     knots = np.asarray(knots, dtype=np.float64)
-    x, M = magwarp_tables(n_samples, knots.shape[-1] - 2)
-    coef = knots @ M.T                                        # (..., (n-1)*4)
-    t = np.arange(n_samples, dtype=np.float64)
-    piece = np.clip(np.searchsorted(x, t, side="right") - 1, 0, x.shape[0] - 2)
-    dt = t - x[piece]
-    c = coef.reshape(knots.shape[:-1] + (x.shape[0] - 1, 4))[..., piece, :]
-    return ((c[..., 0] * dt + c[..., 1]) * dt + c[..., 2]) * dt + c[..., 3]
+    pos, M = magwarp_tables(n_samples, knots.shape[-1] - 2)
+    return _curves(knots @ M.T, pos[:-1], n_samples)           # coefficients (..., (n-1)*4) -> curves

@@ -77,7 +77,12 @@ def test_spline_map_matches_scipy(length, knot):
     got = spline.evaluate(y, length)
     assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-13
     pos, mat = spline.magwarp_tables(length, knot)
-    assert np.array_equal(pos, x) and mat.shape == ((knot + 1) * 4, knot + 2)
+    assert np.array_equal(pos[:-1], x) and mat.shape == ((knot + 1) * 4, knot + 2)
+    # the safe-deviation bound: every curve whose knots stay inside it is positive at every sample
+    safe = pos[-1]
+    assert 0.0 < safe < 1.0
+    worst = 1.0 + safe * np.sign(rng.standard_normal((64, knot + 2)))
+    assert spline.evaluate(worst, length).min() > 5e-4
 
 
 def test_processing_order_is_a_permutation_following_chains():

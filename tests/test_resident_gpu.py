@@ -47,7 +47,10 @@ def _bits(a):
     return a.view(np.uint32)
 
 
-@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)", "(alpha=0.4)durmixmagwarp(0.3,7)"])
+# sigma = 1.5: many warp factors are negative, padding becomes -0.0 and the "factor certainly positive"
+# shortcut of the pipelined kernel must not fire (the comparison is bitwise, so the sign of zero counts)
+@pytest.mark.parametrize("method", ["durratiomixup", "durmixmagwarp(0.2,4)", "(alpha=0.4)durmixmagwarp(0.3,7)",
+                                    "durmixmagwarp(1.5,4)", "durmixmagwarp(0.2,12)"])
 @pytest.mark.parametrize("n_rec,channels,t_len,length", [
     (12, 4, 9001, 2500),     # odd recording length: every row starts at a different 16-byte phase
     (9, 1, 12002, 2500),
