@@ -29,7 +29,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(__file__), "..")))
-from pcgmix_b200 import augmentations, synth  # noqa: E402
+from pcgmix_b200 import augmentations, resident, synth  # noqa: E402
 
 
 # (in, out, halve) per convolution stage; a residual pair follows stages 1 and 3.  Widths, the three
@@ -85,6 +85,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--batch", type=int, default=64, help="per-rank batch (the reference trains with 64)")
+    ap.add_argument("--resident", action="store_true",
+                    help="keep the rank's recordings + cycle table on the GPU and draw batches as table rows "
+                         "(pcgmix_b200.resident): no per-step upload, no padded array")
     opt = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -111,17 +114,31 @@ def main():
         frames = synth.cycle_frames(rng, opt.batch, limit=2500)
         pool.append((torch.from_numpy(synth.cycle_signals(rng, frames, (4,), 2500)).pin_memory(),
                      torch.from_numpy(frames), torch.from_numpy(rng.integers(0, 2, opt.batch))))
+    res = cycle_labels = None
+    if opt.resident:
+        # this rank's recordings (64 x 4 bands x 40 s @ 1 kHz) with dense Springer states -> cycle table, once
+        states = torch.from_numpy(synth.dense_states(rng, 64, 40000, 1000)).to(dev)
+        signal = torch.from_numpy(rng.standard_normal((64, 4, 40000)).astype(np.float32)).to(dev)
+        res = resident.from_dense_states(signal, states, 2500)
+        cycle_labels = rng.integers(0, 2, res.n_cycles)
     aug_dev_ms, aug_host_ms, step_ms = [], [], []
     for step in range(opt.steps):
         host_data, frames, target = pool[step % len(pool)]
+        if opt.resident:
+            ids = rng.integers(0, res.n_cycles, opt.batch)          # what a sampler over the cycle table yields
+            target = torch.from_numpy(cycle_labels[ids])
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        data = host_data.to(dev, non_blocking=True)            # train_model.py:499
+        if not opt.resident:
+            data = host_data.to(dev, non_blocking=True)            # train_model.py:499
         target_ohe = F.one_hot(target, args.num_classes).to(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         h0 = time.perf_counter()
-        data, target_ohe, _, _ = augmentations.augment(args, data, target_ohe, frames, wav, counter, model, dev, None)
+        if opt.resident:
+            data, target_ohe, _, _ = resident.augment(args, res, ids, target_ohe, wav, counter, model, dev, None)
+        else:
+            data, target_ohe, _, _ = augmentations.augment(args, data, target_ohe, frames, wav, counter, model, dev, None)
         aug_host_ms.append((time.perf_counter() - h0) * 1e3)
         e1.record()
         loss = F.cross_entropy(model(data), target_ohe.float().argmax(1))
@@ -140,7 +157,8 @@ def main():
     if rank == 0:
         import json
         ms = float(t.item())
-        print(json.dumps({"config": "cfg5: on-device PCGmix+ -> ResNet9-1D training step, DDP", "n_gpus": world,
+        print(json.dumps({"config": "cfg5: on-device PCGmix+ -> ResNet9-1D training step, DDP" +
+                          (", batches drawn from resident recordings" if opt.resident else ""), "n_gpus": world,
                           "per_rank_batch": opt.batch, "steps": opt.steps, "loss": round(loss.item(), 4),
                           "median_step_ms_max_over_ranks": ms, "augment_call_host_ms_median": float(np.median(aug_host_ms[5:])),
                           "augment_device_span_ms_median": float(np.median(aug_dev_ms[5:])),
