@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
 : > gpurun_out/res_sweep.txt
-for opt in "" "--stages 3" "--stages 5" "--consumer-threads 448" "--pbuf-pct 45 --stages 5" "--max-slice 1252 --stages 6" "--max-slice 1252 --stages 8"; do
+timeout 300 python -m pytest tests/test_resident_gpu.py -m gpu -x -q 2>&1 | tail -3 >> gpurun_out/res_sweep.txt
+for opt in "" "--stages 4" "--stages 2"; do
   echo "== $opt" >> gpurun_out/res_sweep.txt
   timeout 120 python benchmarks/run_configs.py --only resident --reps 100 $opt 2>&1 | python -c "
 import sys,json
