@@ -36,6 +36,36 @@ def main():
         b.copy_(a)
         c.fill_(0.0)
     out["copy_plus_fill_sequential_GBps"] = 3 * gb / (timed(rw2) * 1e-3)
+    # PCIe: one direction at a time and both at once (pinned host memory, 164 MB like one bench batch)
+    m = 4096 * 4 * 2500
+    h_in = torch.empty(m, dtype=torch.float32).pin_memory()
+    h_out = torch.empty(m, dtype=torch.float32).pin_memory()
+    d_in = torch.empty(m, dtype=torch.float32, device="cuda")
+    d_out = torch.empty(m, dtype=torch.float32, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    mb = m * 4 / 1e9
+
+    def h2d():
+        d_in.copy_(h_in, non_blocking=True)
+
+    def d2h():
+        h_out.copy_(d_out, non_blocking=True)
+
+    def both():
+        cur = torch.cuda.current_stream()
+        s1.wait_stream(cur)
+        s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+        cur.wait_stream(s1)
+        cur.wait_stream(s2)
+    out["pcie_h2d_GBps"] = mb / (timed(h2d, 10) * 1e-3)
+    out["pcie_d2h_GBps"] = mb / (timed(d2h, 10) * 1e-3)
+    t_both = timed(both, 10)
+    out["pcie_both_directions_ms_per_164MB_each"] = t_both
+    out["pcie_both_directions_GBps_each"] = mb / (t_both * 1e-3)
     print(json.dumps(out))
 
 
