@@ -358,6 +358,11 @@ def run_b200(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     local_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
+    # Anything a library prints to stdout (NCCL announces its version there) goes to stderr: stdout
+    # carries exactly one JSON line.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     native.load()
@@ -520,6 +525,8 @@ def run_b200(args):
             dev_in[i % NIN].copy_(host_in[i % len(host_in)], non_blocking=True)
             in_ready[i % NIN].record(s_in)
 
+    host_s = [0.0]                                             # wall time spent inside augment() (draws + launch)
+
     def run_e2e(n, seed0):
         for ev in in_free + out_done:
             ev.record(stream)
@@ -531,7 +538,9 @@ def run_b200(args):
             if i + 2 < n:
                 stage_in(i + 2)
             stream.wait_event(in_ready[i % NIN])
+            h0 = time.perf_counter()
             out, _, _, _ = augmentations.augment(a, dev_in[i % NIN], ohe_t[j], frames_t[j], wav, _Step(seed0 + i), None, dev, None)
+            host_s[0] += time.perf_counter() - h0
             in_free[i % NIN].record(stream)
             done = torch.cuda.Event()
             done.record(stream)
@@ -552,6 +561,7 @@ def run_b200(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     wall0 = time.perf_counter()
     e0.record(stream)
+    host_s[0] = 0.0
     run_e2e(E, 20_000 + rank * E)
     e1.record(stream)
     torch.cuda.synchronize()
@@ -562,6 +572,15 @@ def run_b200(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * E * B / (float(te.item()) * 1e-3)
     e2e_launches = native.launch_count - launches_e2e0
+    # the host share of a step on its own (no GPU involved): the draws augment() makes for one batch
+    t_h = time.perf_counter()
+    for rep in range(5):
+        m_ = draws.pairing(args.method, batches[0][2], wav, 30_000 + rep)
+        draws.lambda_pair_fp32(draws.draw_lambda(plan.alpha, 30_000 + rep))
+        if magwarp:
+            draws.draw_knots(B, plan.knot, C, plan.sigma)
+        m_.astype(np.int32)
+    host_draws_ms = (time.perf_counter() - t_h) / 5 * 1e3
     in_bytes = B * C * L * 4
     small_bytes = B * 5 * 4 + B * 4 * 2 + (B * (plan.knot + 2) * C * 8 if magwarp else 0)
 
@@ -605,6 +624,8 @@ def run_b200(args):
                              "cycles_per_s_per_gpu": B / (statistics.fmean(serial_ms) * 1e-3)}},
             "e2e": {"value": e2e_value, "unit": UNIT, "steps": E, "ms_per_step": float(te.item()) / E,
                     "h2d_bytes_per_step": in_bytes + small_bytes, "d2h_bytes_per_step": in_bytes + B * 8,
+                    "host_ms_per_step_inside_augment": 1e3 * host_s[0] / E,      # includes waiting for the batch's H2D copy
+                    "host_draws_ms_per_step": host_draws_ms,                     # pairing + lambda + knots alone, rank 0
                     "api": "pcgmix_b200.augmentations.augment (host draws + 1 kernel) inside a prefetching loop: pinned host in/out, "
                            "H2D of steps k+1, k+2 and D2H of step k-1 on side streams"},
             "gpu_launches": gpu_launches, "gpu_launches_overlapped": overlapped, "gpu_launches_e2e": e2e_launches,
@@ -612,7 +633,8 @@ def run_b200(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -152,6 +152,12 @@ def main():
     t_seg, t_mix = bench.cpu_baseline_cfg1(states.cpu().numpy(), signal.cpu().numpy(), labels1, L1)
     emit("cfg1/CPU port: segmentation + cut (once) and durratiomixup per call", n_cyc, t_mix * 1e3, t_mix * 1e3,
          note="segmentation+cut %.1f ms; mix %.2f ms per call on the host (torch-CPU tensors like the reference)" % (t_seg * 1e3, t_mix * 1e3))
+    # the same batch without the intermediate padded array: recordings + cycle table -> fused cut + pad + mix
+    res1 = resident.ResidentCycles(signal, table, L1, n_cyc, torch.zeros(1, dtype=torch.int32, device=dev))
+    scratch1 = torch.empty((n_cyc, 8), dtype=torch.int32, device=dev)
+    ms, mn = timed(lambda i: resident.mix_rows(res1, None, mix1, 0.3, 0.7, out=out1, scratch=scratch1), args.reps)
+    emit("cfg1/durratiomixup fused with cut + pad (pcgmix_mix1d_resident, 2 launches)", n_cyc, ms, mn,
+         note="replaces cut_cycles + durratiomixup above")
     graph = torch.cuda.CUDAGraph()
     side = torch.cuda.Stream()
     with torch.cuda.stream(side):
