@@ -222,3 +222,66 @@ def test_full_size_batch_property():
     sub_mix = np.arange(256, 512)
     want = orc.mix_batch_vectorised(x, fr, np.concatenate([sub_mix, np.arange(256)]), orc.lambda_as_float32(orc.draw_lambda(1.0, 2)))[:256]
     assert np.array_equal(_bits(got[sl].cpu().numpy()), _bits(want))
+
+
+def test_processing_order_changes_nothing():
+    """`order` only decides which slots are in flight together; the result must not depend on it."""
+    from pcgmix_b200 import draws, resident
+    res, _, _, rng = _resident(17, 10, 4, 20000, 2500)
+    batch = 300
+    ids = torch.from_numpy(rng.integers(0, res.n_cycles, batch).astype(np.int32)).cuda()
+    mix_host = draws.same_label_pairing(rng.integers(0, 2, batch), 5)
+    mix = torch.from_numpy(mix_host.astype(np.int32)).cuda()
+    lam = draws.lambda_pair_fp32(0.42)
+    knots = torch.from_numpy(rng.normal(1.0, 0.2, (batch, 6, 4))).cuda()
+    plain = resident.mix_rows(res, ids, mix, lam[0], lam[1], knots, 4)
+    for order in (draws.processing_order(mix_host), rng.permutation(batch).astype(np.int32)):
+        got = resident.mix_rows(res, ids, mix, lam[0], lam[1], knots, 4, order_dev=torch.from_numpy(np.asarray(order, np.int32)).cuda())
+        assert torch.equal(got, plain)
+    res.check()
+
+
+def test_recordings_beyond_two_to_the_31_elements():
+    """Element indices into the recordings are 64-bit: cycles cut from the far end of a 2.4 G-element
+    tensor (9.7 GB) must come out exactly like cycles cut from a small copy of that region."""
+    from pcgmix_b200 import draws, resident
+    free, _ = torch.cuda.mem_get_info()
+    if free < 24 * 2 ** 30:
+        pytest.skip("needs ~10 GB of free device memory")
+    rng = np.random.default_rng(8)
+    t_len, length = 805_306_371, 2500                                   # 3 recordings x 1 channel: 2 415 919 113 elements
+    big = torch.zeros((3, 1, t_len), dtype=torch.float32, device="cuda")
+    tail = 40_000
+    region = torch.from_numpy(rng.standard_normal(tail).astype(np.float32)).cuda()
+    big[2, 0, t_len - tail:] = region                                   # the last 40 000 samples of the last recording
+    small = torch.zeros((3, 1, tail), dtype=torch.float32, device="cuda")
+    small[2, 0] = region
+    rows_small, pos = [], 3
+    while pos + 1600 < tail:
+        d = rng.integers([90, 150, 70, 300], [160, 400, 130, 900])
+        f = np.concatenate([[0], np.cumsum(d)])
+        rows_small.append([2, pos, pos + int(f[4]), *f.tolist()])
+        pos += int(f[4]) + int(rng.integers(0, 7))
+    rows_small[-1][2] = tail                                            # the last cycle ends with the tensor
+    rows_small[-1][7] = tail - rows_small[-1][1]
+    rows_small[-1][3:7] = [0, 1, 2, 3]
+    rows_big = [[r[0], r[1] + t_len - tail, r[2] + t_len - tail, *r[3:]] for r in rows_small]
+    n = len(rows_small)
+    mix = torch.from_numpy(rng.permutation(n).astype(np.int32)).cuda()
+    lam = draws.lambda_pair_fp32(0.3)
+    knots = torch.from_numpy(rng.normal(1.0, 0.2, (n, 6, 1))).cuda()
+    want = resident.mix_rows(_hand_made_dev(small, rows_small, length), None, mix, lam[0], lam[1], knots, 4)
+    res_big = _hand_made_dev(big, rows_big, length)
+    got = resident.mix_rows(res_big, None, mix, lam[0], lam[1], knots, 4)
+    assert int(res_big.err_flag.item()) == 0
+    assert torch.equal(got, want)
+    assert torch.equal(res_big.padded(), _hand_made_dev(small, rows_small, length).padded())
+
+
+def _hand_made_dev(signal_dev, rows, length):
+    from pcgmix_b200 import resident, segmentation
+    dev = signal_dev.device
+    table = segmentation.CycleTable(torch.tensor(rows, dtype=torch.int32, device=dev),
+                                    torch.tensor([0, len(rows)], dtype=torch.int32, device=dev),
+                                    torch.zeros(1, dtype=torch.int32, device=dev))
+    return resident.ResidentCycles(signal_dev, table, length, len(rows), torch.zeros(1, dtype=torch.int32, device=dev))
