@@ -143,7 +143,7 @@ def _grouped_permutation(keys: Sequence, step: int) -> np.ndarray:
     if isinstance(step, (int, np.integer)) and step >= 0:
         try:
             from . import native
-            _, inverse = np.unique(np.asarray(keys), return_inverse=True)
+            _, inverse = np.unique(keys if isinstance(keys, np.ndarray) else np.asarray(keys), return_inverse=True)
             return native.host_group_permutation(inverse.reshape(-1), int(inverse.max()) + 1 if inverse.size else 0, int(step))
         except (native.NativeLibraryError, OSError):
             pass
@@ -163,7 +163,10 @@ def _grouped_permutation_python(keys: Sequence, step: int) -> np.ndarray:
 def same_label_pairing(labels: np.ndarray, step: int) -> np.ndarray:
     """Default pairing: a seeded permutation inside every class, classes visited in order of first
     appearance, each from a fresh ``Random(step)`` (augmentations.py:500-514)."""
-    return _grouped_permutation(np.asarray(labels).reshape(-1).tolist(), step)
+    labels = np.asarray(labels).reshape(-1)
+    if labels.dtype.kind in "iub":
+        return _grouped_permutation(labels, step)              # class ids: no detour through Python objects
+    return _grouped_permutation(labels.tolist(), step)
 
 
 def pairing(method: str, labels: np.ndarray, wav, step: int) -> np.ndarray:

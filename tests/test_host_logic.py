@@ -198,3 +198,23 @@ def test_native_pairing_replays_cpython_random_sample():
     assert np.array_equal(draws._grouped_permutation(["x"], 3), [0])
     labels = rng.integers(0, 2, 4096)
     assert np.array_equal(draws.same_label_pairing(labels, 77), orc.same_label_mix_indices(labels, 77))
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/pcgmix_b200.h must be usable from C (the boundary is a C ABI): compile a C99 translation
+    unit that includes it and takes the address of every declared entry point."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    header = open(os.path.join(ROOT, "include", "pcgmix_b200.h")).read()
+    names = sorted(set(re.findall(r"^(?:int|long long|const char\*)\s+(pcgmix_\w+)\s*\(", header, flags=re.M)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "pcgmix_b200.h"\nconst void* const entry_points[] = {\n'
+                   + "".join(f"    (const void*)&{n},\n" for n in names) + "};\n"
+                   "int version_macro = PCGMIX_B200_VERSION;\n")
+    out = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic-errors", "-Wno-pedantic", "-I",
+                          os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "abi.o")],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
