@@ -143,7 +143,9 @@ struct PipeArgs {
     int pbuf_cap;              // floats reserved for the packed partner windows of a slice
     int stages;
     int stage_bytes;
-    int header_bytes;          // barriers, knot tables and (PCGmix+) the coefficient matrix
+    int header_bytes;          // barriers, knot tables and (PCGmix+) the coefficient matrix and table
+    int coef_items;            // PCGmix+: the spline coefficients of every CTA's first coef_items items are worked
+                               // out by the whole CTA before the pipeline starts (table behind the matrix)
     int debug;                 // profiling only: 1 = skip stores, 2 = skip arithmetic, 4 = skip partner copies
 };
 
@@ -213,6 +215,9 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     // that fill the whole GPU (so at most two of them are ever in flight) and whose buffers are
     // disjoint.  Harmless when nothing depends on us.
     if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    const int n_coef_all = (a.K + 1) * 4;
+    double* s_tab = s_mat + n_coef_all * (a.K + 2);            // coefficient table, see the consumer branch
 
     if (threadIdx.x >= NCT + 32) {
         // ===================================== producer warp =====================================
@@ -286,7 +291,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             bad0 = static_cast<unsigned>(p0) >= static_cast<unsigned>(a.B);
             if (bad0) p0 = b0;
             load_offsets(b0, p0, f1, f2, wn);
-            y0 = knot_of(b0, row_of(c0));
+            if (RESIDENT || pw >= pa.coef_items) y0 = knot_of(b0, row_of(c0));
         }
         if (n_it > pw + NP) {
             b1 = cycle_of(c1);
@@ -310,7 +315,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 bad1 = static_cast<unsigned>(p1) >= static_cast<unsigned>(a.B);
                 if (bad1) p1 = b1;
                 load_offsets(b1, p1, f1, f2, wn);
-                y0 = knot_of(b1, row_of(c1));
+                if (RESIDENT || it + NP >= pa.coef_items) y0 = knot_of(b1, row_of(c1));
             }
             int p2 = 0, b3 = 0;
             if (it + 2 * NP < n_it) {
@@ -325,12 +330,13 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             // coefficient i = sum_j M[i][j] * knot_j; knot_j comes from lane j by shuffle.  Lane l owns
             // coefficients l, l+32, l+64, l+96; all but the first exist only for knot > 7.
             double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            const bool tabled = MAGWARP && !RESIDENT && it < pa.coef_items;      // coefficients already in the CTA's table
             if constexpr (MAGWARP) {
                 const int n_knots = a.K + 2;
                 const int n_coef = (a.K + 1) * 4;
                 const bool wide = n_coef > 32;
                 const double* mrow = s_mat + lane * n_knots;
-                for (int j = 0; j < ((pa.debug & 8) ? 0 : n_knots); ++j) {
+                for (int j = 0; j < ((pa.debug & 8) || tabled ? 0 : n_knots); ++j) {
                     const double yj = __shfl_sync(kFullMask, y_cur, j);
                     if (lane < n_coef) acc0 = fma(mrow[j], yj, acc0);
                     if (wide) {
@@ -345,7 +351,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             // (exact +0.0f) without evaluating the spline.
             int row_positive = 0;
             if constexpr (RESIDENT && MAGWARP) {
-                const float dev = lane < a.K + 2 ? fabsf(static_cast<float>(y_cur) - 1.0f) : 0.0f;
+                const float dev = lane < a.K + 2 ? fabsf(static_cast<float>(y_cur) - 1.0f) : 0.0f;   // (no table in this variant)
                 row_positive = __reduce_max_sync(kFullMask, __float_as_uint(dev)) < safe_dev_bits ? 1 : 0;
             }
             const int f1n = __shfl_down_sync(kFullMask, f1_cur, 1);
@@ -438,7 +444,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 const unsigned bad = (bad_partner ? PCGMIX_ERR_BAD_PARTNER : 0u) | (bad_frames ? PCGMIX_ERR_BAD_FRAMES : 0u);
                 if (bad != 0u && rest == 0 && a.err != nullptr) atomicOr(a.err, static_cast<int>(bad));
             }
-            if constexpr (MAGWARP) {
+            if (MAGWARP && !tabled) {
                 const int n_coef = (a.K + 1) * 4;
                 if (lane < n_coef) meta->coef[lane] = acc0;
                 if (lane + 32 < n_coef) meta->coef[lane + 32] = acc1;
@@ -488,6 +494,38 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     } else {
         // ===================================== consumer warps ====================================
         const int ct = threadIdx.x;
+        // PCGmix+: the coefficients of this CTA's items (coefficient matrix times the row's knots) are independent
+        // of everything else, so the consumer warps build them up front, while the producers already fill the
+        // first stages (nothing can be consumed for the first microsecond anyway) — instead of one producer warp
+        // doing it item by item inside its dependent chain (measured: 6 us of 62 per launch).  Same fma order as
+        // the producer's per-item path, which remains for items beyond the table.
+        if constexpr (MAGWARP && !RESIDENT) {
+            const int n_knots = a.K + 2;
+            const int tab_items = min(n_it, pa.coef_items);
+            // (item indices fit 32 bits: the launcher checks n_items < 2^31; loops kept rolled: this runs once)
+            auto row_of_item = [&](int q, int& b) {
+                const unsigned item = blockIdx.x + static_cast<unsigned>(q) * gridDim.x;
+                const unsigned rest = item / static_cast<unsigned>(a.B);
+                const int slot = static_cast<int>(item - rest * static_cast<unsigned>(a.B));
+                b = a.order ? __ldg(a.order + slot) : slot;
+                return static_cast<int>(pa.slices_per_row == 1 ? rest : rest / static_cast<unsigned>(pa.slices_per_row));
+            };
+#pragma unroll 1
+            for (int task = threadIdx.x; task < tab_items * n_coef_all; task += NCT) {
+                const int q = task / n_coef_all;
+                const int i = task - q * n_coef_all;
+                int b;
+                const int row = row_of_item(q, b);
+                const double* y = a.knots + static_cast<size_t>(b) * n_knots * a.R + row;
+                const double* m = s_mat + i * n_knots;
+                double acc = 0.0;
+#pragma unroll 1
+                for (int j = 0; j < n_knots; ++j) acc = fma(m[j], __ldg(y + static_cast<size_t>(j) * a.R), acc);
+                s_tab[task] = acc;
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(NCT) : "memory");      // consumers only; producers and the store warp are long gone
+        }
+
         // With one slice per row a thread sees the same columns in every item, so which spline piece
         // they fall into (and the offset from the piece's knot) is found once, not once per vector.
         const bool fixed_cols = pa.slices_per_row == 1;
@@ -514,6 +552,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             const int nvec = meta->nvec;
             const int t_beg = meta->t_beg;
             const float* pbase = meta->pbase;
+            const double* coef = (MAGWARP && !RESIDENT && it < pa.coef_items) ? s_tab + static_cast<size_t>(it) * n_coef_all : meta->coef;
             const float* obuf = stage_o(stage);
             const float* own_g = RESIDENT ? meta->own_g : nullptr;
             const int own_n = RESIDENT ? meta->own_n : 0;
@@ -609,8 +648,8 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                             if (!(t + 3 < s_kint[piece + 1])) piece = -1;
                         }
                         if (__builtin_expect(piece >= 0, 1)) {
-                            const double2 c01 = *reinterpret_cast<const double2*>(&meta->coef[piece * 4]);
-                            const double2 c23 = *reinterpret_cast<const double2*>(&meta->coef[piece * 4 + 2]);
+                            const double2 c01 = *reinterpret_cast<const double2*>(&coef[piece * 4]);
+                            const double2 c23 = *reinterpret_cast<const double2*>(&coef[piece * 4 + 2]);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 const double de = dt + static_cast<double>(e);
@@ -624,7 +663,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                                 int pe = min(static_cast<int>(__umulhi(static_cast<unsigned>(te), a.piece_magic)), a.K);
                                 while (te >= s_kint[pe + 1]) ++pe;
                                 const double de = int_to_double(te) - s_kpos[pe];
-                                const double* c = &meta->coef[pe * 4];
+                                const double* c = &coef[pe * 4];
                                 const double wv = fma(fma(fma(c[0], de, c[1]), de, c[2]), de, c[3]);
                                 r[e] = static_cast<float>(static_cast<double>(r[e]) * wv);
                             }
@@ -716,12 +755,28 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     const size_t stage_bytes = (static_cast<size_t>(pa.slice_cap) * (resident ? 2 : 1) + (resident ? 8 : 0) + pa.pbuf_cap) * sizeof(float) + meta_bytes;
     pa.stage_bytes = static_cast<int>((stage_bytes + 127) & ~static_cast<size_t>(127));
     const size_t mat_bytes = magwarp ? static_cast<size_t>(a.K + 1) * 4 * (a.K + 2) * sizeof(double) : 0;
-    pa.header_bytes = static_cast<int>((kHeaderBytes + mat_bytes + 127) & ~static_cast<size_t>(127));
-    const size_t smem = pa.header_bytes + static_cast<size_t>(pa.stages) * pa.stage_bytes;
-    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     const long long n_items = static_cast<long long>(a.B) * a.R * pa.slices_per_row;
     if (n_items > 2147483647LL) return cudaErrorInvalidConfiguration;
     pa.n_items = static_cast<int>(n_items);
+    // Coefficient table: as many of a CTA's items as fit into the shared memory the stage rings leave free
+    // without costing a resident CTA (the rest is done item by item by the producers).
+    const size_t bare_smem = ((kHeaderBytes + mat_bytes + 127) & ~static_cast<size_t>(127)) + static_cast<size_t>(pa.stages) * pa.stage_bytes;
+    if (bare_smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    pa.coef_items = 0;
+    if (magwarp && !resident && !(tune.debug & 32)) {   // (RESIDENT is consumer-bound: measured no gain there)
+        const int ctas = static_cast<int>((228 * 1024) / (bare_smem + 1024)) < 1 ? 1 : static_cast<int>((228 * 1024) / (bare_smem + 1024));
+        const size_t budget = (228 * 1024) / ctas - 1024 - 128;                 // what one CTA may use at this occupancy
+        const size_t per_item = static_cast<size_t>(a.K + 1) * 4 * sizeof(double);
+        const long long grid_guess = static_cast<long long>(g_sm_count) * ctas;
+        const long long per_cta = (n_items + grid_guess - 1) / grid_guess;
+        long long fit = budget > bare_smem ? static_cast<long long>((budget - bare_smem) / per_item) : 0;
+        if (fit > per_cta) fit = per_cta;
+        pa.coef_items = static_cast<int>(fit < 0 ? 0 : fit);
+    }
+    const size_t tab_bytes = static_cast<size_t>(pa.coef_items) * static_cast<size_t>(a.K + 1) * 4 * sizeof(double);
+    pa.header_bytes = static_cast<int>((kHeaderBytes + mat_bytes + tab_bytes + 127) & ~static_cast<size_t>(127));
+    const size_t smem = pa.header_bytes + static_cast<size_t>(pa.stages) * pa.stage_bytes;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     pa.debug = tune.debug;
     const int vpt = (tune.vec_per_thread == 1 && !resident) ? 1 : 2;
     const int need = ((slice_len / 4) + vpt - 1) / vpt;                       // consumer threads with work
