@@ -518,3 +518,38 @@ def test_zero_samples_keep_the_sign_the_reference_gives_them(sigma):
     assert np.array_equal(got == 0, zeros)
     if sigma >= 1.5:
         assert np.signbit(want[zeros]).mean() > 0.02          # the case is exercised: negative factors exist
+
+
+@pytest.mark.parametrize("knot", [0, 4, 12, 30])
+@pytest.mark.parametrize("with_order", [False, True])
+def test_coefficient_table_and_per_item_path_agree(kernel_choice, knot, with_order):
+    """In the pipelined kernel the spline coefficients of a CTA's first items come from the table its
+    consumer warps build during pipeline fill, the rest from the producers, item by item; how many fit
+    depends on the knot count.  A launch with many items per CTA crosses that boundary: its result must
+    equal, bit for bit, the direct-load kernel's (which has no table) and a launch with the table disabled."""
+    from pcgmix_b200 import draws, native, spline, synth
+    if kernel_choice != "pipeline":
+        pytest.skip("compares the pipelined kernel against the direct-load one itself")
+    rng = np.random.default_rng(100 + knot)
+    b, c, length = 3000, 4, 2500                      # 12 000 items over 444 CTAs: 27-28 per CTA
+    dev = torch.device("cuda:0")
+    frames = synth.cycle_frames(rng, b, limit=length)
+    data = torch.from_numpy(synth.cycle_signals(rng, frames, (c,), length)).to(dev)
+    f = torch.from_numpy(frames.astype(np.int32)).to(dev)
+    mix_host = draws.same_label_pairing(rng.integers(0, 2, b), knot)
+    mix = torch.from_numpy(mix_host.astype(np.int32)).to(dev)
+    order = torch.from_numpy(draws.processing_order(mix_host)).to(dev) if with_order else None
+    knots = torch.from_numpy(rng.normal(1.0, 0.2, (b, knot + 2, c))).to(dev)
+    pos, mat = spline.magwarp_tables(length, knot)
+    pos_d, mat_d = torch.from_numpy(np.array(pos)).to(dev), torch.from_numpy(np.array(mat)).to(dev)
+    lam = draws.lambda_pair_fp32(0.61)
+    outs = []
+    for use_pipeline, debug in ((True, 0), (True, 32), (False, 0)):      # table, table disabled, direct-load kernel
+        native.set_tuning(use_pipeline=use_pipeline, debug=debug)
+        out = torch.empty_like(data)
+        native.mix1d_magwarp(data, out, f, mix, lam[0], lam[1], knots, mat_d, pos_d, knot, order=order)
+        outs.append(out)
+    native.set_tuning(use_pipeline=True)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0].view(torch.int32), outs[2].view(torch.int32))
+    assert torch.equal(outs[1].view(torch.int32), outs[2].view(torch.int32))
