@@ -106,6 +106,53 @@ def resident_section(args, dev):
         emit("resident/%s fused cut+pad+mix from %d recordings x %d x %d, batch %d x %d" % (name, n_rec, C, Tr, Br, L),
              Br, ms, mn, 4.0 * C * (own + mm + L * Br),
              note="bytes = 4*C*(sum len1 + sum M + B*L); mean cycle %.0f samples of L=%d" % (own / Br, L))
+        if magwarp:
+            # end to end from the host's point of view: per step only the table rows of the batch (16 KB) and the
+            # per-step draws go up; the augmented batch comes back into pinned host memory (bench.py's e2e loop
+            # moves the 164 MB padded batch up as well)
+            class _A:
+                method, batch_size, sample_rate, num_classes = "durmixmagwarp(0.2,4)", Br, 1000, 2
+
+            class _S:
+                count = 0
+            host_out = [torch.empty((Br, C, L), dtype=torch.float32).pin_memory() for _ in range(2)]
+            ids_host = [rr.integers(0, res.n_cycles, Br) for _ in range(4)]
+            ohe = [torch.nn.functional.one_hot(torch.from_numpy(rr.integers(0, 2, Br)), 2).to(dev) for _ in range(4)]
+            s_out = torch.cuda.Stream(dev)
+            done_out = [torch.cuda.Event() for _ in range(2)]
+            cur = torch.cuda.current_stream(dev)
+
+            def e2e_steps(n, download=True):
+                for ev in done_out:
+                    ev.record(cur)
+                for i in range(n):
+                    _S.count = 1000 + i
+                    out, _, _, _ = resident.augment(_A, res, ids_host[i % 4], ohe[i % 4], None, _S, None, dev, None)
+                    if not download:
+                        continue
+                    ready = torch.cuda.Event()
+                    ready.record(cur)
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(ready)
+                        s_out.wait_event(done_out[i % 2])
+                        host_out[i % 2].copy_(out, non_blocking=True)
+                        out.record_stream(s_out)
+                        done_out[i % 2].record(s_out)
+                cur.wait_stream(s_out)
+            import time
+            e2e_steps(3)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e2e_steps(24)
+            torch.cuda.synchronize()
+            ms_e2e = (time.perf_counter() - t0) / 24 * 1e3
+            t0 = time.perf_counter()
+            e2e_steps(24, download=False)
+            torch.cuda.synchronize()
+            ms_host = (time.perf_counter() - t0) / 24 * 1e3
+            emit("resident/durmixmagwarp(0.2,4) end to end: table rows + draws up, augmented batch down to pinned host memory",
+                 Br, ms_e2e, ms_e2e, note="h2d per step: %d B of cycle ids + draws; d2h: %d B; the same loop without the download "
+                 "(host draws + launches only): %.2f ms per step" % (Br * 4, Br * C * L * 4, ms_host))
         if args.only == "resident" and (args.stages or args.ctas_per_sm or args.consumer_threads or args.max_slice or args.pbuf_pct):
             continue
         ms2, mn2 = timed(two_step, 50)
