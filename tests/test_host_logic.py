@@ -218,3 +218,17 @@ def test_header_is_plain_c(tmp_path):
                           os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "abi.o")],
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+def test_resident_path_has_no_cpu_fallback_either():
+    """Recordings, annotations and cycle ids on the CPU must be refused loudly, not processed some other way."""
+    import torch
+    from pcgmix_b200 import resident, segmentation
+    signal = torch.zeros(2, 1, 100)
+    states = torch.ones(2, 100, dtype=torch.int8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        resident.from_dense_states(signal, states, 64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        segmentation.cut_cycles(signal, None, 64, 0)
+    with pytest.raises(TypeError):
+        resident._ids_on_device(np.array([0.5, 1.5]), torch.device("cpu"))
