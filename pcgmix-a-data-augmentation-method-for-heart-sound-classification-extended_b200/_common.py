@@ -49,19 +49,52 @@ def labels_from_one_hot(target_ohe) -> np.ndarray:
 def host_frames(frames, batch: int, limit: int) -> np.ndarray:
     """Validate the CPU ``frames`` tensor and return it as int32 (B, 5).
 
-    The reference slices with these offsets directly; offsets that are not monotone or that
-    exceed the row length make it either raise a shape error or (through Python's negative-index
-    wrap-around) blend unrelated samples.  Here they are rejected up front."""
+    Offsets must be non-negative and non-decreasing (a negative or decreasing offset makes the
+    reference blend unrelated samples through Python's negative-index wrap-around; refused here).
+    Offsets BEYOND the row length are accepted, because the reference accepts them: the data builder
+    keeps cycles longer than the padded length (databuilder.ipynb cells 14/25 print a warning,
+    ``resize`` truncates the samples, the offsets stay) and the reference's slices are clamped to the
+    row.  Whether such a cycle can be blended depends on its partner: see :func:`check_pair_windows`."""
     f = frames.detach().cpu().numpy() if isinstance(frames, torch.Tensor) else np.asarray(frames)
     if not np.issubdtype(f.dtype, np.integer):
         raise TypeError(f"frames must hold integers, got {f.dtype}")
     if f.ndim != 2 or f.shape[0] != batch or f.shape[1] < 5:
         raise ValueError(f"frames must be ({batch}, 5), got {f.shape}")
     f5 = f[:, :5].astype(np.int64)
-    if (f5 < 0).any() or (f5 > limit).any() or (np.diff(f5, axis=1) < 0).any():
-        bad = int(np.nonzero((f5 < 0).any(1) | (f5 > limit).any(1) | (np.diff(f5, axis=1) < 0).any(1))[0][0])
-        raise ValueError(f"frames[{bad}] = {f5[bad].tolist()} is not a monotone offset list inside [0, {limit}]")
+    if (f5 < 0).any() or (f5 > 2 ** 31 - 1).any() or (np.diff(f5, axis=1) < 0).any():
+        bad = int(np.nonzero((f5 < 0).any(1) | (f5 > 2 ** 31 - 1).any(1) | (np.diff(f5, axis=1) < 0).any(1))[0][0])
+        raise ValueError(f"frames[{bad}] = {f5[bad].tolist()} is not a non-negative, non-decreasing int32 offset list")
     return np.ascontiguousarray(f5.astype(np.int32))
+
+
+def clamped_windows(f1: np.ndarray, f2: np.ndarray, limit: int):
+    """Per (cycle, state): the reference's blend slices after Python's slice clamping to the row
+    length (augmentations.py:289-304).  Returns ``(dst_start, src_start, dst_width, src_width)``."""
+    f1 = np.asarray(f1, dtype=np.int64)
+    f2 = np.asarray(f2, dtype=np.int64)
+    n0 = np.minimum(np.diff(f1, axis=1), np.diff(f2, axis=1))
+    a1, a2 = np.minimum(f1[:, :4], limit), np.minimum(f2[:, :4], limit)
+    return a1, a2, np.minimum(f1[:, :4] + n0, limit) - a1, np.minimum(f2[:, :4] + n0, limit) - a2
+
+
+def check_pair_windows(frames_i32: np.ndarray, mix: np.ndarray, limit: int) -> None:
+    """Raise where the reference raises: a cycle whose offsets run past the row length can only be
+    blended with a partner if, state by state, the clamped slices of both have the same width (or an
+    empty destination meets a one-sample source, which broadcasts to nothing).  Any other combination
+    is a shape mismatch in the reference's tensor expression (``RuntimeError``) — except a one-sample
+    source against a wider destination, which torch broadcasts over the whole window; that is refused
+    here too.  Batches whose offsets all lie inside the row (the normal case) return immediately."""
+    if frames_i32.size == 0 or int(frames_i32.max()) <= limit:
+        return
+    f1 = frames_i32[:, :5]
+    _, _, wd, ws = clamped_windows(f1, f1[np.asarray(mix, dtype=np.int64)], limit)
+    bad = (wd != ws) & ~((wd == 0) & (ws == 1))
+    if bad.any():
+        b, s = (int(v[0]) for v in np.nonzero(bad))
+        raise RuntimeError(
+            f"cycle {b} (offsets {f1[b].tolist()}) cannot be blended with its partner {int(mix[b])} "
+            f"(offsets {f1[int(mix[b])].tolist()}) in a row of {limit} samples: state {s} clamps to "
+            f"{int(wd[b, s])} destination and {int(ws[b, s])} source samples (the reference raises a shape mismatch here)")
 
 
 def last_frame(frames) -> np.ndarray:

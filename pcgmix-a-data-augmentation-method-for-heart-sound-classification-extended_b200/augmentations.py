@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import draws, native, spline, staging
-from ._common import host_frames, labels_from_one_hot, require_cuda_batch
+from ._common import check_pair_windows, host_frames, labels_from_one_hot, require_cuda_batch
 
 __all__ = ["augment", "pcgmix_on_device", "prepare_on_device"]
 
@@ -107,7 +107,9 @@ def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RE
     lam32, one_minus = draws.lambda_pair_fp32(lam)
 
     frames_i32 = host_frames(frames, batch, length)
-    uploads = [draws.rand_windows(frames_i32, mix_indices, step) if plan.rand_displacement else frames_i32,
+    if not plan.rand_displacement:
+        check_pair_windows(frames_i32, mix_indices, length)
+    uploads = [draws.rand_windows(frames_i32, mix_indices, step, length) if plan.rand_displacement else frames_i32,
                mix_indices.astype(np.int32),
                draws.processing_order(mix_indices) if use_processing_order else np.zeros(0, np.int32)]
     if plan.branch == "durmixmagwarp":

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import draws, native, staging
-from ._common import host_frames, labels_from_one_hot, last_frame, require_cuda_batch
+from ._common import check_pair_windows, host_frames, labels_from_one_hot, last_frame, require_cuda_batch
 
 __all__ = ["augment"]
 
@@ -34,7 +34,9 @@ def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RE
     mix_indices = draws.same_label_pairing(labels, step)
     lam32, one_minus = draws.lambda_pair_fp32(draws.draw_lambda(1, step))
 
-    uploads = [host_frames(frames, batch, n_time), mix_indices.astype(np.int32)]
+    frames_i32 = host_frames(frames, batch, n_time)
+    check_pair_windows(frames_i32, mix_indices, n_time)
+    uploads = [frames_i32, mix_indices.astype(np.int32)]
     h1 = h2 = 0
     has_tbox = False
     if plan.branch in ("durmixtimemask", "durmixcutout"):

@@ -11,7 +11,14 @@ namespace {
 
 thread_local char g_error[512] = "";
 
+// Kernel-selection knobs (pcgmix_set_tuning).  Written and read under g_tuning_mutex: launches take a copy.
 pcgmix::PipelineTuning g_tuning = {1, 0, 0, 0, 0, 0, 0, 0};
+std::mutex g_tuning_mutex;
+
+pcgmix::PipelineTuning tuning_now() {
+    std::lock_guard<std::mutex> lock(g_tuning_mutex);
+    return g_tuning;
+}
 
 int fail(const char* what) {
     std::snprintf(g_error, sizeof(g_error), "%s", what);
@@ -28,10 +35,13 @@ bool mul_fits_int32(long long a, long long b) { return a * b <= 2147483647LL; }
 int check_mix_common(const float* x, float* out, const int32_t* frames, int32_t frame_stride, const int32_t* mix,
                      int32_t B, int32_t R, int32_t P) {
     if (x == nullptr || out == nullptr || frames == nullptr || mix == nullptr) return fail("null pointer argument");
-    if (x == out) return fail("x and out must not alias (partners read the original samples)");
     if (B < 0 || R <= 0 || P <= 0) return fail("B must be >= 0 and the cycle shape positive");
     if (frame_stride < 5) return fail("frame_stride must be >= 5");
     if (!mul_fits_int32(R, P)) return fail("a cycle must hold fewer than 2^31 samples");
+    // out of place: partners read the original samples, so the two batches must not overlap anywhere
+    const uintptr_t bytes = static_cast<uintptr_t>(B) * static_cast<uintptr_t>(R) * static_cast<uintptr_t>(P) * sizeof(float);
+    const uintptr_t xa = reinterpret_cast<uintptr_t>(x), oa = reinterpret_cast<uintptr_t>(out);
+    if (x == out || (xa < oa + bytes && oa < xa + bytes)) return fail("x and out must not overlap (partners read the original samples)");
     return 0;
 }
 
@@ -54,6 +64,7 @@ __global__ void upload_kernel(const T* __restrict__ src, T* __restrict__ dst, lo
 struct Range { uintptr_t lo, hi; };
 struct LaunchRecord {
     cudaStream_t stream;
+    int device;
     bool valid;
     unsigned long long signature;   // launch geometry of a GPU-filling pipelined grid, 0 otherwise
     Range reads[6];
@@ -63,9 +74,16 @@ struct LaunchRecord {
 bool g_overlap_enabled = false;
 long long g_overlap_launches = 0;       // launches issued with the overlap attribute (diagnostics)
 std::mutex g_overlap_mutex;
-LaunchRecord g_history[8][2];          // up to 8 streams, the last two launches of each
-cudaStream_t g_history_stream[8];
+constexpr int kHistorySlots = 16;
+LaunchRecord g_history[kHistorySlots][2];   // up to 16 (device, stream) pairs, the last two launches of each
+cudaStream_t g_history_stream[kHistorySlots];
+int g_history_device[kHistorySlots];
 int g_history_used = 0;
+
+int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
 
 bool intersects(const Range& a, const Range& b) { return a.lo < b.hi && b.lo < a.hi; }
 
@@ -77,6 +95,7 @@ Range range_of(const void* p, size_t bytes) {
 LaunchRecord record_of(const pcgmix::MixArgs& a, bool magwarp, cudaStream_t stream) {
     LaunchRecord r{};
     r.stream = stream;
+    r.device = current_device();
     r.valid = true;
     const size_t cyc = static_cast<size_t>(a.B) * a.R * a.P * sizeof(float);
     r.write = range_of(a.out, cyc);
@@ -105,10 +124,11 @@ bool overlap_decision(const LaunchRecord& now, bool pipelined, unsigned long lon
     std::lock_guard<std::mutex> lock(g_overlap_mutex);
     int slot = -1;
     for (int i = 0; i < g_history_used; ++i)
-        if (g_history_stream[i] == now.stream) slot = i;
+        if (g_history_stream[i] == now.stream && g_history_device[i] == now.device) slot = i;
     if (slot < 0) {
-        slot = g_history_used < 8 ? g_history_used++ : 0;
+        slot = g_history_used < kHistorySlots ? g_history_used++ : 0;
         g_history_stream[slot] = now.stream;
+        g_history_device[slot] = now.device;
         g_history[slot][0].valid = g_history[slot][1].valid = false;
     }
     LaunchRecord* h = g_history[slot];
@@ -124,23 +144,28 @@ bool overlap_decision(const LaunchRecord& now, bool pipelined, unsigned long lon
 }
 
 void set_signature(cudaStream_t stream, unsigned long long signature, bool overlapped) {
+    const int device = current_device();
     std::lock_guard<std::mutex> lock(g_overlap_mutex);
     for (int i = 0; i < g_history_used; ++i) {
-        if (g_history_stream[i] != stream) continue;
+        if (g_history_stream[i] != stream || g_history_device[i] != device) continue;
         g_history[i][0].signature = signature;
         g_history[i][0].valid = signature != 0ull;                    // only GPU-filling pipelined grids can be overlapped
         if (overlapped) ++g_overlap_launches;
     }
 }
 
-// A launch outside the mix bookkeeping went onto `stream`: the next mix launch there must not overlap anything.
+// A launch outside the mix bookkeeping went onto `stream` (an upload of per-step tables, a cut, a segmentation
+// pass, ...): whatever it wrote may be an input of the next mix launch, so that launch must be ordered
+// normally behind it.  Every entry point that launches anything but a bookkept mix kernel calls this.
 void forget_stream(cudaStream_t stream) {
+    const int device = current_device();
     std::lock_guard<std::mutex> lock(g_overlap_mutex);
     for (int i = 0; i < g_history_used; ++i)
-        if (g_history_stream[i] == stream) g_history[i][0].valid = g_history[i][1].valid = false;
+        if (g_history_stream[i] == stream && g_history_device[i] == device) g_history[i][0].valid = g_history[i][1].valid = false;
 }
 
 cudaError_t dispatch_mix(const pcgmix::MixArgs& a, bool magwarp, bool box, cudaStream_t stream) {
+    const pcgmix::PipelineTuning g_tuning = tuning_now();
     const bool pipelined = g_tuning.enabled && pcgmix::pipeline_applicable(a, box);
     unsigned long long previous = 0ull;
     const bool allowed = overlap_decision(record_of(a, magwarp, stream), pipelined, &previous);
@@ -177,6 +202,7 @@ int pcgmix_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor) 
 int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, int32_t ctas_per_sm, int32_t pbuf_pct,
                       int32_t consumer_threads, int32_t debug) {
     if (stages < 0 || stages > 8 || max_slice < 0 || (max_slice % 4) != 0 || ctas_per_sm < 0) return fail("bad tuning value");
+    std::lock_guard<std::mutex> lock(g_tuning_mutex);
     g_tuning.enabled = use_pipeline ? 1 : 0;
     g_tuning.stages = stages;
     g_tuning.max_slice = max_slice;
@@ -193,7 +219,7 @@ long long pcgmix_overlap_launches(void) { return g_overlap_launches; }
 int pcgmix_set_launch_overlap(int32_t enable) {
     std::lock_guard<std::mutex> lock(g_overlap_mutex);
     g_overlap_enabled = enable != 0;
-    for (int i = 0; i < 8; ++i) g_history[i][0].valid = g_history[i][1].valid = false;
+    for (int i = 0; i < kHistorySlots; ++i) g_history[i][0].valid = g_history[i][1].valid = false;
     return 0;
 }
 
@@ -203,9 +229,11 @@ int pcgmix_copy_small(void* dst, const void* src, int64_t bytes, pcgmix_stream_t
     if (bits & 3u) return fail("copy needs 4-byte aligned pointers and size");
     if (bytes == 0) return 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    forget_stream(st);
     if ((bits & 15u) == 0) {
         const long long n = bytes / 16;
-        const int blocks = static_cast<int>(n / 256 + 1 > 64 ? 64 : n / 256 + 1);
+        const long long cap = bytes > (4ll << 20) ? 1184 : 64;          // large copies: enough loads in flight to fill the link
+        const int blocks = static_cast<int>(n / 256 + 1 > cap ? cap : n / 256 + 1);
         upload_kernel<int4><<<blocks, 256, 0, st>>>(static_cast<const int4*>(src), static_cast<int4*>(dst), n);
     } else {
         const long long n = bytes / 4;
@@ -292,6 +320,7 @@ int pcgmix_segment_dense(const int8_t* states, int32_t R, int32_t T, int32_t dow
     if (R < 0 || T < 0 || downsample < 1 || max_cycles < 0) return fail("bad size argument");
     if (max_cycles > 0 && cycles == nullptr) return fail("null cycles with max_cycles > 0");
     if ((reinterpret_cast<uintptr_t>(cycles) & 15u) != 0) return fail("cycles must be 16-byte aligned");
+    forget_stream(static_cast<cudaStream_t>(stream));
     const cudaError_t e = pcgmix::launch_segment_dense(states, R, T, downsample, cycles, max_cycles, cycle_count,
                                                        err_flag, static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_segment_dense", e);
@@ -305,6 +334,7 @@ int pcgmix_segment_table(const int32_t* positions, const int8_t* codes, const in
     if (spec_cols > 0 && rec_len == nullptr) return fail("rec_len required when spec_cols > 0");
     if (max_cycles > 0 && cycles == nullptr) return fail("null cycles with max_cycles > 0");
     if ((reinterpret_cast<uintptr_t>(cycles) & 15u) != 0) return fail("cycles must be 16-byte aligned");
+    forget_stream(static_cast<cudaStream_t>(stream));
     const cudaError_t e = pcgmix::launch_segment_table(positions, codes, rec_offsets, R, downsample, spec_cols,
                                                        rec_len, cycles, max_cycles, cycle_count, err_flag,
                                                        static_cast<cudaStream_t>(stream));
@@ -316,6 +346,7 @@ int pcgmix_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T, cons
     if (n_cycles < 0 || R < 0 || C < 0 || T < 0 || L < 0) return fail("bad size argument");
     if (n_cycles > 0 && (signal == nullptr || cycles == nullptr || out == nullptr)) return fail("null pointer argument");
     if ((reinterpret_cast<uintptr_t>(cycles) & 15u) != 0) return fail("cycles must be 16-byte aligned");
+    forget_stream(static_cast<cudaStream_t>(stream));
     const cudaError_t e = pcgmix::launch_cut_cycles(signal, R, C, T, cycles, n_cycles, n_cycles_dev, out, L,
                                                     static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_cut_cycles", e);
@@ -349,6 +380,8 @@ int pcgmix_mix1d_resident(const float* signal, int32_t n_rec, int32_t C, int32_t
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
+    const pcgmix::PipelineTuning g_tuning = tuning_now();
+    forget_stream(st);                                         // not part of the overlap bookkeeping of the mix launches
     if (scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 15u) == 0 && g_tuning.enabled &&
         pcgmix::pipeline_applicable(a, false)) {
         // slot records first, then the persistent TMA-pipelined kernel reading them in place of `frames`
@@ -356,7 +389,6 @@ int pcgmix_mix1d_resident(const float* signal, int32_t n_rec, int32_t C, int32_t
         if (e == cudaSuccess) {
             a.frames = scratch;
             a.frame_stride = 8;
-            forget_stream(st);                                 // not part of the overlap bookkeeping of the mix launches
             unsigned long long signature = 0ull;
             e = pcgmix::launch_mix_pipeline(a, magwarp, g_tuning, false, 0ull, st, &signature);
         }
@@ -370,6 +402,7 @@ int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_
                              int32_t* err_flag, pcgmix_stream_t stream) {
     if (n < 0 || fs <= 0 || frame_stride < 5) return fail("bad size argument");
     if (n > 0 && (frames == nullptr || features == nullptr)) return fail("null pointer argument");
+    forget_stream(static_cast<cudaStream_t>(stream));
     const cudaError_t e = pcgmix::launch_duration_features(frames, frame_stride, n, fs, features, err_flag,
                                                            static_cast<cudaStream_t>(stream));
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_duration_features", e);

@@ -55,6 +55,41 @@ struct MixArgs {
     long long n_sig;           // n_rec*R*T_sig
 };
 
+// One heart state of a cycle against the same state of its partner, with the slice clamping of the
+// reference's tensor expression (augmentations.py:289-304, augmentations2d.py:206-221):
+//     d_new[:, f1:f1+n] = d_new[:, f1:f1+n]*lam + d2[:, f2:f2+n]*(1-lam),   n = min(len1, len2)
+// Python slices are clamped to the row length P, so offsets beyond P are legal there (the data builder
+// keeps cycles longer than the padded length: databuilder.ipynb cells 14/25 print a warning and truncate
+// the samples, the offsets stay).  The assignment works when the clamped destination and source
+// slices have equal width (blend that many samples), or when an empty destination meets a one-sample
+// source (broadcast to nothing); every other combination makes the reference raise a shape error —
+// except a one-sample source against a wider destination, which it broadcasts over the window; that
+// case is refused here as well (PCGMIX_ERR_BAD_FRAMES).  Returns false for refused / non-monotone input.
+__device__ __forceinline__ bool pair_window(int f1, int f1n, int f2, int f2n, int P, int& start, int& n, int& shift) {
+    const int len1 = f1n - f1;
+    const int len2 = f2n - f2;
+    const int n0 = min(len1, len2);
+    const int a1 = min(f1, P), e1 = min(f1 + n0, P);
+    const int a2 = min(f2, P), e2 = min(f2 + n0, P);
+    const int wd = e1 - a1, ws = e2 - a2;
+    start = a1;
+    shift = a2 - a1;
+    n = wd == ws ? wd : 0;
+    const bool sane = (f1 >= 0) & (f2 >= 0) & (len1 >= 0) & (len2 >= 0);
+    return sane & ((wd == ws) | ((wd == 0) & (ws == 1)));
+}
+
+// Cycle handled in processing slot `slot`: order[slot], or the slot itself when no order was given.  An entry
+// outside [0, B) is not followed (it would index out of the batch): the slot's own cycle is processed instead
+// and PCGMIX_ERR_BAD_PARTNER is raised.
+__device__ __forceinline__ int cycle_of_slot(const MixArgs& a, int slot) {
+    if (a.order == nullptr) return slot;
+    const int b = __ldg(a.order + slot);
+    if (static_cast<unsigned>(b) < static_cast<unsigned>(a.B)) return b;
+    if (a.err != nullptr) atomicOr(a.err, static_cast<int>(PCGMIX_ERR_BAD_PARTNER));
+    return slot;
+}
+
 // mix_kernels.cu — direct-load kernel (any shape)
 cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t stream);
 

@@ -78,13 +78,13 @@ __device__ __forceinline__ double int_to_double(int i) {
 // Warp 0 builds the cycle's state table: lanes 0..4 fetch the five offsets of the cycle and of
 // its partner, durations / blended lengths / shifts come from warp shuffles (the per-cycle
 // prefix sums are already in the offsets).  Invalid input (partner out of range, offsets not
-// monotone or outside [0,P]) degrades to "copy the cycle" and raises a bit in *err.
+// monotone, or clamped windows of unequal width: see pair_window) degrades to "copy the cycle" and raises a bit in *err.
 __device__ __forceinline__ void build_windows(const MixArgs& a, int b, int4* s_win, int* s_partner, bool report) {
     const int lane = threadIdx.x;
     int p = __ldg(a.mix + b);
     const bool bad_partner = static_cast<unsigned>(p) >= static_cast<unsigned>(a.B);
     if (bad_partner) p = b;
-    int f1 = 0, f2 = 0, n = 0;
+    int f1 = 0, f2 = 0, n = 0, start = 0, shift = 0;
     bool ok;
     if (a.windows != nullptr) {
         // explicit windows (the reference's '(rand)' displacement): {start, length, shift} per state
@@ -97,6 +97,8 @@ __device__ __forceinline__ void build_windows(const MixArgs& a, int b, int4* s_w
         const int next_lo = __shfl_down_sync(kFullMask, f1, 1);
         const int limit = (lane < 3) ? next_lo : a.P;
         ok = (f1 >= 0) & (n >= 0) & (f1 + n <= limit) & (f2 >= 0) & (f2 + n <= a.P);
+        start = f1;
+        shift = f2 - f1;
     } else {
         if (lane < 5) {
             f1 = __ldg(a.frames + static_cast<size_t>(b) * a.frame_stride + lane);
@@ -104,17 +106,14 @@ __device__ __forceinline__ void build_windows(const MixArgs& a, int b, int4* s_w
         }
         const int f1n_ = __shfl_down_sync(kFullMask, f1, 1);
         const int f2n_ = __shfl_down_sync(kFullMask, f2, 1);
-        const int len1 = f1n_ - f1;
-        const int len2 = f2n_ - f2;
-        ok = (f1 >= 0) & (f2 >= 0) & (len1 >= 0) & (len2 >= 0) & (f1n_ <= a.P) & (f2n_ <= a.P);
-        n = min(len1, len2);
+        ok = pair_window(f1, f1n_, f2, f2n_, a.P, start, n, shift);
     }
     const int f1n = __shfl_down_sync(kFullMask, f1, 1);
     const unsigned bad_frames = __ballot_sync(kFullMask, (lane < 4) && !ok);
     if (bad_frames != 0u || bad_partner) n = 0;
     // "next start": the column where the state after s begins; P closes the last one
-    const int next = (lane < 3) ? f1n : a.P;
-    if (lane < 4) s_win[lane] = make_int4(f1, n, f2 - f1, next);
+    const int next = (lane < 3) ? min(f1n, a.P) : a.P;
+    if (lane < 4) s_win[lane] = make_int4(start, n, shift, next);
     if (lane == 0) {
         *s_partner = p;
         const unsigned bad = (bad_partner ? PCGMIX_ERR_BAD_PARTNER : 0u) | (bad_frames ? PCGMIX_ERR_BAD_FRAMES : 0u);
@@ -137,7 +136,7 @@ mix_kernel(const __grid_constant__ MixArgs a) {
     __shared__ int s_lut[ROWS ? 1 : kFlatMaxPitch];
 
     const int slot = blockIdx.x;
-    const int b = a.order ? __ldg(a.order + slot) : slot;
+    const int b = cycle_of_slot(a, slot);
     // first vector of this CTA, in vector units from the start of the cycle, and its column
     int vbeg, vend, row = 0, col0;
     if constexpr (ROWS) {
@@ -389,7 +388,8 @@ cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t
     const bool aligned16 = ((reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.out)) & 15u) == 0;
     const bool rows_fit_grid = a.R <= 65535;
     const bool vec_rows = aligned16 && (a.P % 4) == 0 && rows_fit_grid;
-    const bool vec_flat = aligned16 && (a.n_per_cycle % 4) == 0 && !magwarp && a.P <= kFlatMaxPitch;
+    // (a 4-wide vector of a FLAT slice may touch two rows, not more: rows shorter than a vector go scalar)
+    const bool vec_flat = aligned16 && (a.n_per_cycle % 4) == 0 && !magwarp && a.P <= kFlatMaxPitch && a.P >= 4;
     // One CTA per row slice only pays off for long rows; spectrogram rows (128..250 columns) are
     // handled as slices of the cycle's flat plane, 1024 vectors per CTA.
     const bool long_rows = a.P > kFlatMaxPitch;

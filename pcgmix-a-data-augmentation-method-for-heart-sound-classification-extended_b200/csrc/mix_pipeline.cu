@@ -42,6 +42,8 @@
 // the end of the tensor, a window reaches into the partner's padding, the windows exceed pbuf) are
 // processed sample by sample from global memory — same result.
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace pcgmix {
@@ -245,7 +247,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
             return c;
         };
-        auto cycle_of = [&](Cursor c) { return a.order ? __ldg(a.order + c.slot) : c.slot; };
+        auto cycle_of = [&](Cursor c) { return cycle_of_slot(a, c.slot); };
         auto row_of = [&](Cursor c) { return pa.slices_per_row == 1 ? c.rest : c.rest / pa.slices_per_row; };
         auto knot_of = [&](int b, int row) {                // lane j holds knot j of (cycle b, row)
             double y = 0.0;
@@ -356,21 +358,20 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
             const int f1n = __shfl_down_sync(kFullMask, f1_cur, 1);
             const int f2n = __shfl_down_sync(kFullMask, f2_cur, 1);
-            const int len1 = f1n - f1_cur;
-            const int len2 = f2n - f2_cur;
+            // window of state `lane`: start column, blended samples, shift to the partner's column (pair_window
+            // applies the reference's slice clamping; explicit windows arrive resolved from the host)
+            int wstart = f1_cur, n = wn_cur, d = f2_cur - f1_cur;
             const bool ok = (a.windows != nullptr)
                 ? ((f1_cur >= 0) & (wn_cur >= 0) & (f1_cur + wn_cur <= ((lane < 3) ? f1n : a.P)) & (f2_cur >= 0) & (f2_cur + wn_cur <= a.P))
-                : ((f1_cur >= 0) & (f2_cur >= 0) & (len1 >= 0) & (len2 >= 0) & (f1n <= a.P) & (f2n <= a.P));
+                : pair_window(f1_cur, f1n, f2_cur, f2n, a.P, wstart, n, d);
             const unsigned bad_frames = __ballot_sync(kFullMask, (lane < 4) && !ok);
-            int n = (a.windows != nullptr) ? wn_cur : min(len1, len2);
             if (bad_frames != 0u || bad_partner) n = 0;
-            const int d = f2_cur - f1_cur;
             const int t_beg = slice * pa.slice_len;
             const int t_end = min(t_beg + pa.slice_len, a.P);
             // the part of state `lane`'s blended window that falls into this slice, as a
             // 16-byte-aligned range [src_lo, src_hi) of the partner's row
-            const int w_beg = max(f1_cur, t_beg);
-            const int w_end = min(f1_cur + n, t_end);
+            const int w_beg = max(wstart, t_beg);
+            const int w_end = min(wstart + n, t_end);
             bool have = (lane < 4) && (w_end > w_beg);
             // RESIDENT: where this slot's and the partner's samples of this channel start inside `signal`
             long long own_first = 0, par_first = 0;
@@ -425,9 +426,9 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             const long long prow = RESIDENT ? par_first : (static_cast<long long>(p) * a.R + row) * a.P;
             const float* src_base = RESIDENT ? a.signal : a.x;
             if (lane < 4) {
-                const int next = (lane < 3) ? f1n : a.P;
+                const int next = (lane < 3) ? min(f1n, a.P) : a.P;
                 const int shift = staged ? (t_beg + d - src_lo + off) : d;
-                meta->win[lane] = make_int4(f1_cur - t_beg, n, shift, next - t_beg);
+                meta->win[lane] = make_int4(wstart - t_beg, n, shift, next - t_beg);
             }
             if (lane == 0) {
                 meta->pbase = staged ? pbuf : (src_base + prow + t_beg);
@@ -507,7 +508,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 const unsigned item = blockIdx.x + static_cast<unsigned>(q) * gridDim.x;
                 const unsigned rest = item / static_cast<unsigned>(a.B);
                 const int slot = static_cast<int>(item - rest * static_cast<unsigned>(a.B));
-                b = a.order ? __ldg(a.order + slot) : slot;
+                b = cycle_of_slot(a, slot);
                 return static_cast<int>(pa.slices_per_row == 1 ? rest : rest / static_cast<unsigned>(pa.slices_per_row));
             };
 #pragma unroll 1
@@ -682,18 +683,84 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     }
 }
 
-template <int NCT, int VPT, bool RESIDENT>
-cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, int grid, size_t smem, bool magwarp, bool overlap_previous,
-                       cudaStream_t stream) {
-    // opt in to the large dynamic shared-memory carve-out once per kernel instance
-    static bool allowed[2] = {false, false};
-    if (!allowed[magwarp ? 1 : 0]) {
-        const cudaError_t e = magwarp
-            ? cudaFuncSetAttribute(mix_pipeline_kernel<NCT, true, VPT, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)
-            : cudaFuncSetAttribute(mix_pipeline_kernel<NCT, false, VPT, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+constexpr int kMaxDevices = 64;
+
+// Per-device facts, filled on first use (a process may drive several GPUs: the reference trains with
+// nn.DataParallel, train_model.py:385).
+struct DeviceFacts {
+    int sm_count;
+};
+std::mutex g_device_mutex;
+DeviceFacts g_device[kMaxDevices] = {};
+
+cudaError_t device_facts(int* device, DeviceFacts* facts) {
+    cudaError_t e = cudaGetDevice(device);
+    if (e != cudaSuccess) return e;
+    if (*device < 0 || *device >= kMaxDevices) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    if (g_device[*device].sm_count == 0) {
+        e = cudaDeviceGetAttribute(&g_device[*device].sm_count, cudaDevAttrMultiProcessorCount, *device);
         if (e != cudaSuccess) return e;
-        allowed[magwarp ? 1 : 0] = true;
     }
+    *facts = g_device[*device];
+    return cudaSuccess;
+}
+
+// What a launch still has to decide once the kernel instance (and with it the true CTA residency) is known.
+struct GridPlan {
+    int device;
+    int sm_count;
+    int per_sm_wanted;          // residency the shared-memory / thread budget allows (and the tuning cap)
+    bool overlap_previous;
+    unsigned long long previous_signature;
+    unsigned long long* signature_out;
+};
+
+template <int NCT, bool MAGWARP, int VPT, bool RESIDENT>
+cudaError_t launch_instance(const MixArgs& a, PipeArgs pa, size_t smem, GridPlan plan, cudaStream_t stream) {
+    auto kernel = mix_pipeline_kernel<NCT, MAGWARP, VPT, RESIDENT>;
+    // Per device and kernel instance: opt in to the large dynamic shared-memory carve-out (the attribute is
+    // per device) and ask the runtime how many CTAs of this instance really fit on an SM at this size.
+    struct Cached { bool opted_in; size_t smem; int ctas; };
+    static Cached cache[kMaxDevices] = {};
+    static std::mutex cache_mutex;
+    int resident_ctas = 0;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex);
+        Cached& c = cache[plan.device];
+        if (!c.opted_in) {
+            const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+            if (e != cudaSuccess) return e;
+            c.opted_in = true;
+        }
+        if (c.smem != smem || c.ctas == 0) {
+            int n = 0;
+            const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NCT + kHelperThreads, smem);
+            if (e != cudaSuccess) return e;
+            if (n < 1) return cudaErrorInvalidConfiguration;
+            c.smem = smem;
+            c.ctas = n;
+        }
+        resident_ctas = c.ctas;
+    }
+    const int per_sm = plan.per_sm_wanted < resident_ctas ? plan.per_sm_wanted : resident_ctas;
+    long long grid = static_cast<long long>(plan.sm_count) * per_sm;
+    // Geometry signature: non-zero only for a grid that fills the GPU exactly (as many CTAs as can be resident,
+    // counted by the runtime from registers, threads and shared memory).  Two launches with EQUAL signatures
+    // have the same CTA footprint and count, so the second can only become fully resident after the first has
+    // fully retired: at most two such grids are ever in flight.  Overlap is only allowed then.
+    const unsigned long long signature =
+        (grid <= pa.n_items && per_sm == resident_ctas)
+            ? ((static_cast<unsigned long long>(smem) << 32) ^ (static_cast<unsigned long long>(NCT) << 20) ^
+               (static_cast<unsigned long long>(MAGWARP) << 30) ^ static_cast<unsigned long long>(grid)) : 0ull;
+    if (plan.signature_out != nullptr) *plan.signature_out = signature;
+    bool overlap = plan.overlap_previous;
+    if (!RESIDENT && (signature == 0ull || signature != plan.previous_signature)) overlap = false;
+    if (grid > pa.n_items) grid = pa.n_items;
+    pa.step_rest = static_cast<int>(grid / a.B);
+    pa.step_slot = static_cast<int>(grid % a.B);
+    pa.stepn_rest = static_cast<int>((grid * kProducerWarps) / a.B);
+    pa.stepn_slot = static_cast<int>((grid * kProducerWarps) % a.B);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
     cfg.blockDim = dim3(NCT + kHelperThreads);
@@ -703,12 +770,15 @@ cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, int grid, size_t sm
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = overlap_previous ? 1 : 0;
-    return magwarp ? cudaLaunchKernelEx(&cfg, mix_pipeline_kernel<NCT, true, VPT, RESIDENT>, a, pa)
-                   : cudaLaunchKernelEx(&cfg, mix_pipeline_kernel<NCT, false, VPT, RESIDENT>, a, pa);
+    cfg.numAttrs = overlap ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, a, pa);
 }
 
-int g_sm_count = 0;
+template <int NCT, int VPT, bool RESIDENT>
+cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, size_t smem, bool magwarp, const GridPlan& plan, cudaStream_t stream) {
+    return magwarp ? launch_instance<NCT, true, VPT, RESIDENT>(a, pa, smem, plan, stream)
+                   : launch_instance<NCT, false, VPT, RESIDENT>(a, pa, smem, plan, stream);
+}
 
 }  // namespace
 
@@ -730,13 +800,10 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
         const double scaled = ratio * 4294967296.0 * (1.0 - 1e-9);
         a.piece_magic = scaled >= 4294967295.0 ? 4294967295u : static_cast<unsigned>(scaled);
     }
-    if (g_sm_count == 0) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-    }
+    int device = 0;
+    DeviceFacts facts{};
+    if (const cudaError_t e = device_facts(&device, &facts)) return e;
+    const int g_sm_count = facts.sm_count;
     PipeArgs pa{};
     const int max_slice = tune.max_slice > 0 ? (tune.max_slice > 3584 ? 3584 : tune.max_slice) : 3584;   // 448 threads x 2 vectors
     pa.slices_per_row = (a.P + max_slice - 1) / max_slice;
@@ -791,51 +858,38 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     const int by_threads = 2048 / (nct + kHelperThreads);
     per_sm = per_sm < by_threads ? per_sm : by_threads;
     if (tune.ctas_per_sm > 0 && tune.ctas_per_sm < per_sm) per_sm = tune.ctas_per_sm;
-    long long grid = static_cast<long long>(g_sm_count) * per_sm;
-    // Geometry signature: non-zero only for a grid that fills the GPU.  Two launches with EQUAL signatures
-    // have the same CTA footprint and CTA count, so the second can only become fully resident after the
-    // first has fully retired: at most two such grids are ever in flight.  Overlap is only allowed then.
-    const unsigned long long signature =
-        grid <= pa.n_items ? ((static_cast<unsigned long long>(smem) << 32) ^ (static_cast<unsigned long long>(nct) << 20) ^
-                              static_cast<unsigned long long>(grid)) : 0ull;
-    if (full_grid_signature != nullptr) *full_grid_signature = signature;
-    if (signature == 0ull || signature != previous_signature) overlap_previous = false;
-    if (grid > pa.n_items) grid = pa.n_items;
-    pa.step_rest = static_cast<int>(grid / a.B);
-    pa.step_slot = static_cast<int>(grid % a.B);
-    pa.stepn_rest = static_cast<int>((grid * kProducerWarps) / a.B);
-    pa.stepn_slot = static_cast<int>((grid * kProducerWarps) % a.B);
     if (pa.stages < kProducerWarps) return cudaErrorInvalidConfiguration;
-    const int g = static_cast<int>(grid);
+    GridPlan plan{device, g_sm_count, per_sm, overlap_previous, previous_signature, full_grid_signature};
     if (resident) {
         // launched with the programmatic attribute: the kernel right before it on the stream is the slot-record
         // kernel, which lets it start early; the producers wait for the records (griddepcontrol.wait)
+        plan.overlap_previous = true;
         switch (nct) {
-            case 128: return launch_nct<128, 2, true>(a, pa, g, smem, magwarp, true, stream);
-            case 192: return launch_nct<192, 2, true>(a, pa, g, smem, magwarp, true, stream);
-            case 256: return launch_nct<256, 2, true>(a, pa, g, smem, magwarp, true, stream);
-            case 320: return launch_nct<320, 2, true>(a, pa, g, smem, magwarp, true, stream);
-            case 384: return launch_nct<384, 2, true>(a, pa, g, smem, magwarp, true, stream);
-            default: return launch_nct<448, 2, true>(a, pa, g, smem, magwarp, true, stream);
+            case 128: return launch_nct<128, 2, true>(a, pa, smem, magwarp, plan, stream);
+            case 192: return launch_nct<192, 2, true>(a, pa, smem, magwarp, plan, stream);
+            case 256: return launch_nct<256, 2, true>(a, pa, smem, magwarp, plan, stream);
+            case 320: return launch_nct<320, 2, true>(a, pa, smem, magwarp, plan, stream);
+            case 384: return launch_nct<384, 2, true>(a, pa, smem, magwarp, plan, stream);
+            default: return launch_nct<448, 2, true>(a, pa, smem, magwarp, plan, stream);
         }
     }
     if (vpt == 1) {
         switch (nct) {
-            case 128: return launch_nct<128, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-            case 192: return launch_nct<192, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-            case 256: return launch_nct<256, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-            case 320: return launch_nct<320, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-            case 384: return launch_nct<384, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-            default: return launch_nct<448, 1, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+            case 128: return launch_nct<128, 1, false>(a, pa, smem, magwarp, plan, stream);
+            case 192: return launch_nct<192, 1, false>(a, pa, smem, magwarp, plan, stream);
+            case 256: return launch_nct<256, 1, false>(a, pa, smem, magwarp, plan, stream);
+            case 320: return launch_nct<320, 1, false>(a, pa, smem, magwarp, plan, stream);
+            case 384: return launch_nct<384, 1, false>(a, pa, smem, magwarp, plan, stream);
+            default: return launch_nct<448, 1, false>(a, pa, smem, magwarp, plan, stream);
         }
     }
     switch (nct) {
-        case 128: return launch_nct<128, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-        case 192: return launch_nct<192, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-        case 256: return launch_nct<256, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-        case 320: return launch_nct<320, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-        case 384: return launch_nct<384, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
-        default: return launch_nct<448, 2, false>(a, pa, g, smem, magwarp, overlap_previous, stream);
+        case 128: return launch_nct<128, 2, false>(a, pa, smem, magwarp, plan, stream);
+        case 192: return launch_nct<192, 2, false>(a, pa, smem, magwarp, plan, stream);
+        case 256: return launch_nct<256, 2, false>(a, pa, smem, magwarp, plan, stream);
+        case 320: return launch_nct<320, 2, false>(a, pa, smem, magwarp, plan, stream);
+        case 384: return launch_nct<384, 2, false>(a, pa, smem, magwarp, plan, stream);
+        default: return launch_nct<448, 2, false>(a, pa, smem, magwarp, plan, stream);
     }
 }
 

@@ -113,14 +113,12 @@ __device__ __forceinline__ void build_windows_resident(const MixArgs& a, int b, 
     if (__ballot_sync(kFullMask, !rec_ok) != 0u) bad_index = true;
     const int f1n = __shfl_down_sync(kFullMask, f1, 1);
     const int f2n = __shfl_down_sync(kFullMask, f2, 1);
-    const int len1 = f1n - f1;
-    const int len2 = f2n - f2;
-    const bool ok = (f1 >= 0) & (f2 >= 0) & (len1 >= 0) & (len2 >= 0) & (f1n <= a.P) & (f2n <= a.P);
-    int n = min(len1, len2);
+    int start = 0, n = 0, shift = 0;
+    const bool ok = pair_window(f1, f1n, f2, f2n, a.P, start, n, shift);
     const unsigned bad_frames = __ballot_sync(kFullMask, (lane < 4) && !ok);
     if (bad_frames != 0u || bad_index) n = 0;
-    const int next = (lane < 3) ? f1n : a.P;
-    if (lane < 4) s_win[lane] = make_int4(f1, n, f2 - f1, next);
+    const int next = (lane < 3) ? min(f1n, a.P) : a.P;
+    if (lane < 4) s_win[lane] = make_int4(start, n, shift, next);
     if (lane == 0) {
         *s_partner_row = partner_row;
         const unsigned bad = (bad_index ? PCGMIX_ERR_BAD_PARTNER : 0u) | (bad_frames ? PCGMIX_ERR_BAD_FRAMES : 0u);
@@ -138,7 +136,7 @@ mix_resident_kernel(const __grid_constant__ MixArgs a) {
     __shared__ int s_kint[MAGWARP ? kMaxPieces + 1 : 1];
 
     const int slot = blockIdx.x;
-    const int b = a.order ? __ldg(a.order + slot) : slot;
+    const int b = cycle_of_slot(a, slot);
     const int row = blockIdx.z;
     const int seg_beg = blockIdx.y * a.chunk_len;                     // vector units within the row
     const int seg_end = min(seg_beg + a.chunk_len, a.P / VEC);

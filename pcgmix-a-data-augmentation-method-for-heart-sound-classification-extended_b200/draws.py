@@ -143,6 +143,9 @@ def _grouped_permutation(keys: Sequence, step: int) -> np.ndarray:
     if isinstance(step, (int, np.integer)) and step >= 0:
         try:
             from . import native
+        except (ImportError, OSError):
+            return _grouped_permutation_python(keys, step)
+        try:
             _, inverse = np.unique(keys if isinstance(keys, np.ndarray) else np.asarray(keys), return_inverse=True)
             return native.host_group_permutation(inverse.reshape(-1), int(inverse.max()) + 1 if inverse.size else 0, int(step))
         except (native.NativeLibraryError, OSError):
@@ -206,14 +209,16 @@ def mask_geometry(step: int, region_max: float):
     return gap, frac1
 
 
-def rand_windows(frames: np.ndarray, mix: np.ndarray, step: int) -> np.ndarray:
+def rand_windows(frames: np.ndarray, mix: np.ndarray, step: int, limit: Optional[int] = None) -> np.ndarray:
     """Blended windows of the reference's ``(rand)`` variant (augmentations.py:305-337), as
     ``(B, 4, 3)`` int32 ``{start in the cycle, blended length, shift to the partner's sample}``.
 
     Per state the shorter of the two durations is blended, placed at a seeded offset inside the
     longer one: ``disp = random.Random(step).randint(0, |len2 - len1|)`` from a FRESH generator, so
     it depends only on the gap; if the partner's state is longer the offset moves the read window
-    in the partner, otherwise it moves the write window in the cycle."""
+    in the partner, otherwise it moves the write window in the cycle.  With ``limit`` (the row
+    length) the windows are clamped like the reference's slices; unequal clamped widths raise like the
+    reference's tensor expression does."""
     f1 = np.asarray(frames, dtype=np.int64)[:, :5]
     f2 = f1[np.asarray(mix, dtype=np.int64)]
     len1, len2 = np.diff(f1, axis=1), np.diff(f2, axis=1)
@@ -224,7 +229,17 @@ def rand_windows(frames: np.ndarray, mix: np.ndarray, step: int) -> np.ndarray:
     disp = np.vectorize(table.__getitem__, otypes=[np.int64])(np.abs(gap))
     dst = f1[:, :4] + np.where(gap < 0, disp, 0)
     src = f2[:, :4] + np.where(gap >= 0, disp, 0)
-    out = np.stack([dst, np.minimum(len1, len2), src - dst], axis=2)
+    n = np.minimum(len1, len2)
+    if limit is not None and f1.size and int(f1.max()) > limit:
+        d0, s0 = np.minimum(dst, limit), np.minimum(src, limit)
+        wd, ws = np.minimum(dst + n, limit) - d0, np.minimum(src + n, limit) - s0
+        bad = (wd != ws) & ~((wd == 0) & (ws == 1))
+        if bad.any():
+            b, s = (int(v[0]) for v in np.nonzero(bad))
+            raise RuntimeError(f"cycle {b}, state {s}: the displaced windows clamp to {int(wd[b, s])} destination and "
+                               f"{int(ws[b, s])} source samples in a row of {limit} (the reference raises a shape mismatch here)")
+        dst, src, n = d0, s0, np.where(wd == ws, wd, 0)
+    out = np.stack([dst, n, src - dst], axis=2)
     return np.ascontiguousarray(out.astype(np.int32))
 
 

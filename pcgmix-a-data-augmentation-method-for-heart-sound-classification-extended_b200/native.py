@@ -29,7 +29,7 @@ _c_f32 = ctypes.c_float
 _ptr = ctypes.c_void_p
 
 # name -> argtypes; restype is int for all but pcgmix_last_error.  Mirrors include/pcgmix_b200.h
-# (tests/test_abi.py checks the two against each other).
+# (tests/test_host_logic.py checks the two against each other).
 SIGNATURES = {
     "pcgmix_version": [],
     "pcgmix_last_error": [],
@@ -131,6 +131,14 @@ def _frames_ptr(frames):
         raise ValueError("frames rows must be unit-stride with a row stride >= 5")
     stride = frames.stride(0) if frames.shape[0] > 1 else max(5, frames.stride(0))
     return frames.data_ptr(), int(stride)
+
+
+def _check_rows(batch: int, **tables):
+    """Per-cycle tables must cover the batch: the kernels index them with cycle ids up to ``batch - 1``
+    (the entries themselves are range-checked on the device)."""
+    for name, t in tables.items():
+        if t is not None and (t.dim() < 1 or t.shape[0] < batch):
+            raise ValueError(f"{name} has {t.shape[0] if t.dim() else 0} rows, the batch has {batch} cycles")
 
 
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
@@ -240,6 +248,7 @@ def mix1d(x, out, frames, mix, lam32, one_minus_lam32, order=None, err_flag=None
     if x.dim() != 3 or out.shape != x.shape:
         raise ValueError("x and out must be (B, C, L) of equal shape")
     B, C, L = x.shape
+    _check_rows(B, frames=frames, mix=mix, order=order)
     dev = _same_device(x, out, frames, mix, order, err_flag)
     fptr, fstride = _frames_ptr(frames)
     with _on_device(dev):
@@ -263,6 +272,7 @@ def mix1d_magwarp(x, out, frames, mix, lam32, one_minus_lam32, knots, coefmat, k
         raise ValueError(f"knots must be (B, knot+2, C) = {(B, knot + 2, C)}, got {tuple(knots.shape)}")
     if tuple(coefmat.shape) != ((knot + 1) * 4, knot + 2) or tuple(knot_pos.shape) != (knot + 3,):
         raise ValueError("coefmat / knot_pos do not match knot")
+    _check_rows(B, frames=frames, mix=mix, order=order)
     dev = _same_device(x, out, frames, mix, order, err_flag, knots, coefmat, knot_pos)
     fptr, fstride = _frames_ptr(frames)
     with _on_device(dev):
@@ -288,6 +298,7 @@ def mix1d_windows(x, out, windows, mix, lam32, one_minus_lam32, knots=None, coef
         raise ValueError(f"windows must be (B, 4, 3), got {tuple(windows.shape)}")
     if knots is not None and tuple(knots.shape) != (B, knot + 2, C):
         raise ValueError("knots must be (B, knot+2, C)")
+    _check_rows(B, mix=mix, order=order)
     dev = _same_device(x, out, windows, mix, order, err_flag, knots, coefmat, knot_pos)
     with _on_device(dev):
         rc = load().pcgmix_mix1d_windows(
@@ -314,6 +325,7 @@ class PreparedMix1D:
         if x.dim() != 3 or out.shape != x.shape:
             raise ValueError("x and out must be (B, C, L) of equal shape")
         B, C, L = x.shape
+        _check_rows(B, frames=frames, mix=mix, order=order)
         self._keep = (x, out, frames, mix, knots, coefmat, knot_pos, order, err_flag)
         self._device = _same_device(x, out, frames, mix, order, err_flag, knots, coefmat, knot_pos)
         fptr, fstride = _frames_ptr(frames)
@@ -335,8 +347,9 @@ class PreparedMix1D:
     def launch(self, stream_handle=None):
         global launch_count
         if stream_handle is None:
-            stream_handle = torch.cuda.current_stream(self._device).cuda_stream
-        rc = self._fn(*self._args, stream_handle)
+            stream_handle = _stream_handle(self._device)
+        with _on_device(self._device):                     # no-op when the tensors' device already is current
+            rc = self._fn(*self._args, stream_handle)
         if rc != 0:
             _check(rc, self._name)
         launch_count += self._count
@@ -348,6 +361,7 @@ def mix2d(x, out, frames, mix, lam32, one_minus_lam32, tbox=None, h1=0, h2=0, or
     if x.dim() != 4 or out.shape != x.shape:
         raise ValueError("x and out must be (B, Ch, F, T) of equal shape")
     B, Ch, F, T = x.shape
+    _check_rows(B, frames=frames, mix=mix, order=order, tbox=tbox)
     dev = _same_device(x, out, frames, mix, order, err_flag, tbox)
     fptr, fstride = _frames_ptr(frames)
     with _on_device(dev):
@@ -415,6 +429,9 @@ def mix1d_resident(signal, cycles, sel, mix, lam32, one_minus_lam32, out, knots=
         raise ValueError(f"out has {C_out} channels, the recordings have {C}")
     if cycles.dim() != 2 or cycles.shape[1] != 8 or not cycles.is_contiguous():
         raise ValueError("cycles must be a contiguous (n, 8) int32 cycle table")
+    _check_rows(B, sel=sel, mix=mix, order=order, knots=knots)
+    if knots is not None and tuple(knots.shape) != (B, knot + 2, C):
+        raise ValueError(f"knots must be (B, knot+2, C) = {(B, knot + 2, C)}, got {tuple(knots.shape)}")
     dev = _same_device(signal, cycles, sel, mix, out, knots, coefmat, knot_pos, order, err_flag, scratch)
     if scratch is not None and (scratch.numel() < 8 * B or not scratch.is_contiguous()):
         raise ValueError("scratch must be a contiguous int32 tensor of at least B*8 elements")

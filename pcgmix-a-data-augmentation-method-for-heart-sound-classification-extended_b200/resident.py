@@ -57,13 +57,14 @@ class ResidentCycles:
         return self.table.cycles[_ids_on_device(ids, self.signal.device).long(), 3:].cpu().to(torch.int64)
 
     def check(self):
-        """Raise if a mix launch met a table row, recording or partner out of range, or offsets
-        outside [0, L] (synchronises)."""
+        """Raise if a mix launch met a table row, recording or partner out of range, or offsets the
+        reference could not have blended (synchronises)."""
         flag = int(self.err_flag.item())
         if flag & native.ERR_BAD_PARTNER:
             raise IndexError("a cycle id, recording index or partner index was out of range")
         if flag & native.ERR_BAD_FRAMES:
-            raise ValueError(f"a cycle's state offsets are not monotone inside [0, {self.length}]")
+            raise ValueError(f"a cycle's state offsets are decreasing, or its windows and its partner's clamp to unequal "
+                             f"widths in a row of {self.length} samples (the reference raises a shape mismatch there)")
         return self
 
 

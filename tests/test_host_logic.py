@@ -7,6 +7,7 @@ import re
 
 import numpy as np
 import pytest
+import torch
 
 from oracle import pcgmix_oracle as orc
 from pcgmix_b200 import build_native, draws, native, sharding, spline, synth
@@ -232,3 +233,39 @@ def test_resident_path_has_no_cpu_fallback_either():
         segmentation.cut_cycles(signal, None, 64, 0)
     with pytest.raises(TypeError):
         resident._ids_on_device(np.array([0.5, 1.5]), torch.device("cpu"))
+
+
+def test_clamped_window_rule_predicts_the_reference(golden):
+    """`_common.clamped_windows` / `check_pair_windows` (and `pair_window` in csrc/common.cuh, which
+    states the same rule) against what the unmodified reference did with every ordered pair of the
+    long-cycle offset lists: it blends iff every state's clamped widths agree, an empty destination
+    meets one source sample, or one source sample is broadcast over a wider destination (refused here)."""
+    from pcgmix_b200 import _common
+    g = golden("long_pairs_1d")
+    fr, ok, L = g["frames"], g["ok"], g["data"].shape[-1]
+    n_broadcast = 0
+    for i in range(len(fr)):
+        for j in range(len(fr)):
+            _, _, wd, ws = _common.clamped_windows(fr[i:i + 1], fr[j:j + 1], L)
+            fine = (wd == ws) | ((wd == 0) & (ws == 1))
+            broadcast = (ws == 1) & (wd > 1)
+            assert bool((fine | broadcast).all()) == bool(ok[i, j]), (i, j)
+            pair = np.stack([fr[i], fr[j]]).astype(np.int32)
+            if fine.all():
+                _common.check_pair_windows(pair, np.array([1, 1]), L)
+            else:
+                n_broadcast += bool(ok[i, j])
+                with pytest.raises(RuntimeError):
+                    _common.check_pair_windows(pair, np.array([1, 1]), L)
+    assert n_broadcast == 5
+
+
+def test_host_frames_accepts_offsets_beyond_the_row_and_rejects_disorder():
+    from pcgmix_b200 import _common
+    ok = _common.host_frames(torch.tensor([[0, 10, 20, 30, 70], [0, 5, 9, 12, 40]]), 2, 50)
+    assert ok.dtype == np.int32 and ok[0, 4] == 70
+    for bad in ([[0, 10, 9, 30, 40]], [[-1, 10, 20, 30, 40]], [[0, 10, 20, 30, 2 ** 31]]):
+        with pytest.raises(ValueError):
+            _common.host_frames(torch.tensor(bad), 1, 50)
+    with pytest.raises(TypeError):
+        _common.host_frames(torch.tensor([[0.0, 1, 2, 3, 4]]), 1, 50)

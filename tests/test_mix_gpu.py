@@ -240,16 +240,22 @@ def test_lambda_one_and_special_values():
 
 
 def test_invalid_frames_are_rejected_on_host_and_flagged_on_device():
-    from pcgmix_b200 import augmentations, native
+    from pcgmix_b200 import augmentations, draws, native
     dev = torch.device("cuda:0")
     d = torch.randn(2, 1, 32, device=dev)
     ohe = torch.nn.functional.one_hot(torch.tensor([0, 0]), 2).to(dev)
     bad = torch.tensor([[0, 10, 5, 20, 30], [0, 5, 10, 20, 30]])
     with pytest.raises(ValueError):
         augmentations.augment(_Args("durratiomixup", 2), d, ohe, bad, ["a"] * 2, _Step(1), None, dev, None)
+    # offsets past the row end are legal when the clamped windows agree (the reference's slices clamp) ...
     too_long = torch.tensor([[0, 5, 10, 20, 40], [0, 5, 10, 20, 30]])
-    with pytest.raises(ValueError):
-        augmentations.augment(_Args("durratiomixup", 2), d, ohe, too_long, ["a"] * 2, _Step(1), None, dev, None)
+    out, _, mix, _ = augmentations.augment(_Args("durratiomixup", 2), d, ohe, too_long, ["a"] * 2, _Step(1), None, dev, None)
+    want = orc.mix_batch(d.cpu().numpy(), too_long.numpy(), mix, draws.lambda_pair_fp32(draws.draw_lambda(1, 1))[0])
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+    # ... and a shape mismatch, as in the reference, when they do not
+    clash = torch.tensor([[0, 5, 10, 20, 40], [0, 5, 10, 25, 45]])
+    with pytest.raises(RuntimeError):
+        augmentations.augment(_Args("durratiomixup", 2), d, ohe, clash, ["a"] * 2, _Step(0), None, dev, None)
     # device-resident frames cannot be validated on the host: the kernel copies the cycle and flags it
     err = torch.zeros(1, dtype=torch.int32, device=dev)
     out = torch.empty_like(d)
@@ -553,3 +559,143 @@ def test_coefficient_table_and_per_item_path_agree(kernel_choice, knot, with_ord
     torch.cuda.synchronize()
     assert torch.equal(outs[0].view(torch.int32), outs[2].view(torch.int32))
     assert torch.equal(outs[1].view(torch.int32), outs[2].view(torch.int32))
+
+
+# ---- cycles whose offsets run past the row end (fixtures from the unmodified reference) ----------------
+def _all_pairs_launch(x, fr, lam, two_d=False):
+    """cycle k = (i, j) mixes row i with partner row n*n + j, one launch; returns (out[n, n, ...], err)."""
+    from pcgmix_b200 import native
+    n = x.shape[0]
+    data = np.concatenate([np.repeat(x, n, axis=0), x], axis=0)
+    frames = np.concatenate([np.repeat(fr, n, axis=0), fr], axis=0).astype(np.int32)
+    mix = np.concatenate([n * n + np.tile(np.arange(n), n), np.arange(n * n, n * n + n)]).astype(np.int32)
+    dev = torch.device("cuda:0")
+    d = torch.from_numpy(data).to(dev)
+    out = torch.empty_like(d)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    fn = native.mix2d if two_d else native.mix1d
+    fn(d, out, torch.from_numpy(frames).to(dev), torch.from_numpy(mix).to(dev), lam, np.float32(1) - lam, err_flag=err)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()[: n * n].reshape((n, n) + x.shape[1:]), int(err.item())
+
+
+@pytest.mark.parametrize("tag", ["1d", "2d"])
+def test_long_cycle_pairs_vs_reference_fixture(golden, tag):
+    """Where the reference blends, the kernel blends bit-exactly; where it raises a shape mismatch (or
+    broadcasts one partner sample over a window), the kernel copies the cycle and raises BAD_FRAMES."""
+    from pcgmix_b200 import _common, native
+    g = golden(f"long_pairs_{tag}")
+    x, fr, ok = g["data"], g["frames"], g["ok"]
+    n, length = x.shape[0], x.shape[-1]
+    got, err = _all_pairs_launch(x, fr, np.float32(g["lam"]), two_d=tag == "2d")
+    assert err == native.ERR_BAD_FRAMES
+    blended = 0
+    for i in range(n):
+        for j in range(n):
+            _, _, wd, ws = _common.clamped_windows(fr[i:i + 1], fr[j:j + 1], length)
+            if ((wd == ws) | ((wd == 0) & (ws == 1))).all():
+                assert ok[i, j]
+                assert np.array_equal(got[i, j].view(np.uint32), g["out"][i, j].view(np.uint32)), (i, j)
+                blended += 1
+            else:
+                assert np.array_equal(got[i, j].view(np.uint32), x[i].view(np.uint32)), (i, j)
+    assert blended == 23
+
+
+def test_long_cycle_pairs_in_long_rows():
+    """The same offset lists scaled to rows of 1500 samples, so that the pipelined kernel takes them
+    (its producer derives the windows itself); expected values from the oracle's slice semantics."""
+    from pcgmix_b200 import native
+    rng = np.random.default_rng(77)
+    base = np.array([[0, 10, 20, 30, 40], [0, 10, 20, 30, 70], [0, 12, 24, 36, 50], [0, 10, 20, 55, 60],
+                     [0, 60, 70, 80, 90], [0, 5, 10, 15, 120], [2, 9, 21, 33, 52]], dtype=np.int64)
+    fr = base * 30 + np.array([0, 1, 2, 3, 1])              # odd shifts between the pairs
+    length, lam = 1500, np.float32(0.41)
+    x = rng.standard_normal((fr.shape[0], 2, length)).astype(np.float32)
+    got, err = _all_pairs_launch(x, fr, lam)
+    n_ok = 0
+    for i in range(len(fr)):
+        for j in range(len(fr)):
+            try:
+                want = orc.mix_pair(x[i], x[j], fr[i], fr[j], lam)
+                n_ok += 1
+            except ValueError:
+                want = x[i]
+            assert np.array_equal(got[i, j].view(np.uint32), want.view(np.uint32)), (i, j)
+    assert 0 < n_ok < len(fr) ** 2 and err == native.ERR_BAD_FRAMES
+
+
+def test_long_cycle_batch_vs_reference_fixture(golden):
+    g = golden("long_batch_1d")
+    out, _, mix, _ = _run_1d("durratiomixup", int(g["step"]), g["data"], g["labels"], g["frames"])
+    assert np.array_equal(mix, g["mix"])
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), g["out_durratiomixup"].view(np.uint32))
+    out, _, mix, _ = _run_1d("durmixmagwarp(0.2,4)", int(g["step"]), g["data"], g["labels"], g["frames"])
+    assert _rel_err(out.cpu().numpy(), g["out_durmixmagwarp"]) <= REL_TOL
+    with pytest.raises(RuntimeError):
+        _run_1d("durratiomixup", int(g["step_raises"]), g["data"], g["labels"], g["frames"])
+
+
+def test_order_entries_out_of_range_are_flagged_not_followed():
+    from pcgmix_b200 import native, synth
+    rng = np.random.default_rng(8)
+    b, c, length = 6, 2, 1200
+    frames = synth.cycle_frames(rng, b, limit=length)
+    x = synth.cycle_signals(rng, frames, (c,), length)
+    dev = torch.device("cuda:0")
+    d = torch.from_numpy(x).to(dev)
+    guard = torch.full((b + 2, c, length), 3.0, device=dev)
+    out = guard[1:b + 1]
+    mix = np.array([1, 0, 3, 2, 5, 4], np.int32)
+    order = torch.tensor([0, 1, 99, 3, -4, 5], dtype=torch.int32, device=dev)      # slots 2 and 4 name no cycle
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    lam = np.float32(0.3)
+    native.mix1d(d, out, torch.from_numpy(frames.astype(np.int32)).to(dev), torch.from_numpy(mix).to(dev), lam,
+                 np.float32(1) - lam, order=order, err_flag=err)
+    torch.cuda.synchronize()
+    assert int(err.item()) & native.ERR_BAD_PARTNER
+    want = orc.mix_batch(x, frames, mix, lam)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))   # the slot's own cycle was processed
+    assert torch.all(guard[0] == 3.0) and torch.all(guard[-1] == 3.0)
+
+
+def test_tables_shorter_than_the_batch_are_refused():
+    from pcgmix_b200 import native
+    dev = torch.device("cuda:0")
+    d = torch.zeros(4, 1, 64, device=dev)
+    out = torch.empty_like(d)
+    fr = torch.zeros(4, 5, dtype=torch.int32, device=dev)
+    with pytest.raises(ValueError):
+        native.mix1d(d, out, fr, torch.zeros(3, dtype=torch.int32, device=dev), 0.5, 0.5)
+    with pytest.raises(ValueError):
+        native.mix1d(d, out, fr[:2], torch.zeros(4, dtype=torch.int32, device=dev), 0.5, 0.5)
+    with pytest.raises(ValueError):
+        native.mix1d(d, out, fr, torch.zeros(4, dtype=torch.int32, device=dev), 0.5, 0.5,
+                     order=torch.zeros(2, dtype=torch.int32, device=dev))
+    with pytest.raises(RuntimeError):                                            # overlapping views of one buffer
+        buf = torch.zeros(5, 1, 64, device=dev)
+        native.mix1d(buf[:4], buf[1:], fr, torch.zeros(4, dtype=torch.int32, device=dev), 0.5, 0.5)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """The reference trains single-process multi-GPU (nn.DataParallel, train_model.py:385): the library keeps
+    its per-device facts (shared-memory opt-in, SM count, launch history) apart."""
+    from pcgmix_b200 import synth
+    rng = np.random.default_rng(12)
+    b, c, length = 64, 4, 2500
+    frames = synth.cycle_frames(rng, b, limit=length)
+    x = synth.cycle_signals(rng, frames, (c,), length)
+    labels = rng.integers(0, 2, b)
+    from pcgmix_b200 import augmentations
+    for rep in range(2):
+        for index in (0, 1):
+            dev = torch.device("cuda", index)
+            ohe = torch.nn.functional.one_hot(torch.from_numpy(labels), 2).to(dev)
+            for method in ("durratiomixup", "durmixmagwarp(0.2,4)"):
+                out, _, mix, _ = augmentations.augment(_Args(method, b), torch.from_numpy(x).to(dev), ohe, torch.from_numpy(frames),
+                                                       ["a"] * b, _Step(3 + rep), None, dev, None)
+                torch.cuda.synchronize(dev)
+                want, want_mix, _, _ = orc.augment_1d(method, x, labels, frames, 3 + rep)
+                assert out.device == dev and np.array_equal(mix, want_mix)
+                assert _rel_err(out.cpu().numpy(), want) <= REL_TOL

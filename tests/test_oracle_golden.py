@@ -107,3 +107,30 @@ def test_mix_lambda_one_is_identity_and_no_fma():
     got = orc.mix_batch(x, fr, mix, lam)
     expect = x * lam + x[mix] * (np.float32(1) - lam)
     assert np.array_equal(got[..., :280], expect[..., :280])
+
+
+# ---- cycles whose offsets run past the row (tests/golden/make_golden_long_cycles.py) ------------------
+@pytest.mark.parametrize("tag", ["1d", "2d"])
+def test_long_cycle_pairs_blend_or_raise_like_the_reference(golden, tag):
+    g = golden(f"long_pairs_{tag}")
+    x, fr, ok = g["data"], g["frames"], g["ok"]
+    assert ok.sum() == 28 and not ok.all()
+    for i in range(x.shape[0]):
+        for j in range(x.shape[0]):
+            if ok[i, j]:
+                got = orc.mix_pair(x[i], x[j], fr[i], fr[j], np.float32(g["lam"]))
+                assert np.array_equal(got.view(np.uint32), g["out"][i, j].view(np.uint32)), (i, j)
+            else:
+                with pytest.raises(ValueError):
+                    orc.mix_pair(x[i], x[j], fr[i], fr[j], np.float32(g["lam"]))
+
+
+def test_long_cycle_batch_matches_reference(golden):
+    g = golden("long_batch_1d")
+    assert (g["frames"][:, 4] > g["data"].shape[-1]).sum() == 4
+    for method in ("durratiomixup", "durmixmagwarp(0.2,4)"):
+        out, mix, _, _ = orc.augment_1d(method, g["data"].copy(), g["labels"], g["frames"], int(g["step"]))
+        assert np.array_equal(mix, g["mix"])
+        assert np.array_equal(out.view(np.uint32), g["out_" + method.split("(")[0]].view(np.uint32))
+    with pytest.raises(ValueError):
+        orc.augment_1d("durratiomixup", g["data"].copy(), g["labels"], g["frames"], int(g["step_raises"]))

@@ -141,7 +141,8 @@ def _two_step(res, mix, lam, knots=None, knot=0):
 def test_cycles_touching_the_end_of_the_tensor_and_too_long_cycles(warp):
     """Rows that end exactly at the last element of a tensor whose size is not a multiple of 4 (the
     aligned loads must not run past it), a cycle clipped by the end of its recording, and cycles longer
-    than L (offsets outside [0, L]: copied unmixed and flagged, like the two-step path)."""
+    than L: blended where the clamped windows agree (like the reference's slices), copied unmixed and
+    flagged where they do not — like the two-step path."""
     from pcgmix_b200 import draws, resident
     rng = np.random.default_rng(3)
     t_len, length = 3001, 1200
@@ -150,20 +151,26 @@ def test_cycles_touching_the_end_of_the_tensor_and_too_long_cycles(warp):
         [1, 2301, 3001, 0, 100, 300, 400, 700],      # ends at the very last element of the tensor
         [0, 2303, 3001, 0, 120, 280, 410, 698],      # ends at the end of recording 0
         [1, 5, 905, 0, 90, 350, 460, 900],
-        [0, 2, 1502, 0, 200, 600, 800, 1500],        # longer than L -> flagged, copied
+        [0, 2, 1502, 0, 200, 600, 800, 1500],        # longer than L, blends with a short partner (and as partner of row 4)
         [1, 2500, 3400, 0, 100, 400, 500, 900],      # table says 900 samples, the recording has 501: rest is padding
         [0, 1000, 1000, 0, 0, 0, 0, 0],              # empty cycle
+        [1, 0, 1600, 0, 200, 600, 900, 1600],        # longer than L against long row 3: clamped widths differ -> flagged, copied
     ]
     res = _hand_made(signal, rows, length)
-    mix = torch.tensor([1, 2, 4, 0, 3, 4], dtype=torch.int32, device="cuda")
+    mix = torch.tensor([1, 2, 4, 0, 3, 4, 3], dtype=torch.int32, device="cuda")
     lam = draws.lambda_pair_fp32(0.37)
-    knots = torch.from_numpy(rng.normal(1.0, 0.2, (6, 6, 1))).cuda() if warp else None
+    knots = torch.from_numpy(rng.normal(1.0, 0.2, (7, 6, 1))).cuda() if warp else None
     got = resident.mix_rows(res, None, mix, lam[0], lam[1], knots, 4)
     want, flag = _two_step(res, mix, lam, knots, 4)
     assert np.array_equal(_bits(got.cpu().numpy()), _bits(want.cpu().numpy()))
     assert int(res.err_flag.item()) == flag and flag != 0
     with pytest.raises(ValueError):
         res.check()
+    if not warp:                                                                  # the long row really was blended
+        padded = res.padded().cpu().numpy()
+        want3 = orc.mix_pair(padded[3], padded[0], np.array(rows[3][3:]), np.array(rows[0][3:]), lam[0])
+        assert np.array_equal(_bits(got[3].cpu().numpy()), _bits(want3))
+        assert np.array_equal(_bits(got[6].cpu().numpy()), _bits(padded[6]))
 
 
 def test_out_of_range_rows_and_partners_are_flagged_not_followed():
