@@ -253,6 +253,26 @@ int pcgmix_copy_small(void* dst, const void* src, int64_t bytes, pcgmix_stream_t
 int pcgmix_host_group_permutation(const int64_t* group, int64_t n, int64_t n_groups, uint64_t seed,
                                   int64_t* mix);
 
+/*
+ * Host-side replay of the reference's lambda and magnitude-warp knot draws from NumPy's legacy global stream
+ * (augmentations.py:659-666 get_lambda, :677 magnitude_warp):
+ *     np.random.seed(seed); lam = np.random.beta(alpha, alpha); knots = np.random.normal(1.0, sigma, n_knots)
+ * *lam_out and knots_out[n_knots] receive bit-identical values.  state_out[624] / *pos_out / *has_gauss_out /
+ * *gauss_out (all optional) receive the generator state NumPy would be left in (np.random.get_state()), so a
+ * caller can mirror the reference's side effect on the global stream.  max_threads bounds the worker threads used
+ * for the log/sqrt pass of large draws.  Returns non-zero (and draws nothing) when seed > 2^32-1 (NumPy refuses
+ * such seeds) or alpha <= 0 (the reference then neither re-seeds nor draws lambda: use NumPy's stream as it is).
+ */
+int pcgmix_host_lambda_knots(uint64_t seed, double alpha, double sigma, int64_t n_knots, int32_t max_threads,
+                             double* lam_out, double* knots_out, uint32_t* state_out, int32_t* pos_out,
+                             int32_t* has_gauss_out, double* gauss_out);
+
+/*
+ * order[k] = cycles in pairing-chain order (b, mix[b], mix[mix[b]], ... for b = 0, 1, ... not yet visited): the
+ * processing order that keeps a cycle read as "partner" in L2 until it is read as "itself".  Host code.
+ */
+int pcgmix_host_processing_order(const int64_t* mix, int64_t n, int32_t* order);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,11 +22,30 @@ def require_cuda_batch(data, ndim: int, what: str):
 _label_slots = {}
 
 
+def with_host_labels(target_ohe, target):
+    """Attach the loader's CPU ``target`` (class id per cycle, what ``F.one_hot`` was built from:
+    train_model.py:500-501) to the device one-hot tensor and return that tensor.
+
+    The reference recovers the class ids from the DEVICE tensor every step (``target_ohe.max(1)[1].cpu()``,
+    augmentations.py:501), which makes the host wait for everything queued on the GPU.  A caller that
+    still has the CPU ``target`` can hand it over this way; ``augment`` then pairs from it without any
+    device synchronisation.  The ids must be what the arg-max of ``target_ohe`` would give."""
+    ids = target.detach().cpu().numpy() if isinstance(target, torch.Tensor) else np.asarray(target)
+    if ids.ndim != 1 or ids.shape[0] != target_ohe.shape[0] or not np.issubdtype(ids.dtype, np.integer):
+        raise ValueError("target must be a 1-D integer array with one class id per cycle")
+    target_ohe.pcgmix_host_labels = ids.astype(np.int64)
+    return target_ohe
+
+
 def labels_from_one_hot(target_ohe) -> np.ndarray:
     """Class id per cycle, as the reference recovers it (augmentations.py:501): arg-max of the
     one-hot target, read back to the host.  On a CUDA tensor the read-back is a tiny kernel writing
     into pinned host memory followed by an event wait, not a ``.cpu()`` copy: a copy-engine transfer
-    would wait behind any large device->host copy in flight (results of the previous step)."""
+    would wait behind any large device->host copy in flight (results of the previous step).  No
+    device work at all when the caller attached the CPU ids (:func:`with_host_labels`)."""
+    attached = getattr(target_ohe, "pcgmix_host_labels", None)
+    if attached is not None and attached.shape[0] == target_ohe.shape[0]:
+        return attached
     idx = target_ohe.max(1, keepdim=True)[1].reshape(-1)
     if not idx.is_cuda:
         return idx.detach().numpy()

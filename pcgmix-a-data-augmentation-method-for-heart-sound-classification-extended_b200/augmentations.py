@@ -19,15 +19,19 @@ import numpy as np
 import torch
 
 from . import draws, native, spline, staging
-from ._common import check_pair_windows, host_frames, labels_from_one_hot, require_cuda_batch
+from ._common import check_pair_windows, host_frames, labels_from_one_hot, require_cuda_batch, with_host_labels
 
-__all__ = ["augment", "pcgmix_on_device", "prepare_on_device"]
+__all__ = ["augment", "pcgmix_on_device", "prepare_on_device", "with_host_labels"]
 
 # Visit the cycles in pairing-chain order (draws.processing_order) so that a cycle read as
 # "partner" is still in L2 when it is read as "itself".  Worth ~3 % of kernel time when batches are
 # device-resident; it costs ~1 ms of host Python per 4096 cycles, so the per-step drop-in call, which
 # is bound by the host and by PCIe, leaves it off unless asked.
 use_processing_order = False
+
+# PCGmix+: start drawing step k+1's lambda and knots on a worker thread while step k runs (the seed is the step
+# count).  Pure overlap; results and NumPy's global stream are the same with it on or off.
+prefetch_next_step = True
 
 _table_cache = {}
 
@@ -103,7 +107,15 @@ def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RE
     batch, channels, length = data.shape
     labels = labels_from_one_hot(target_ohe)
     mix_indices = draws.pairing(args.method, labels, wav, step)
-    lam = draws.draw_lambda(plan.alpha, step)
+    knots = None
+    if plan.branch == "durmixmagwarp":
+        if plan.knot > native.MAX_KNOT:
+            raise ValueError(f"durmixmagwarp knot={plan.knot} exceeds the supported maximum {native.MAX_KNOT}")
+        lam, knots = draws.lambda_and_knots(plan.alpha, step, batch, plan.knot, channels, plan.sigma)
+        if prefetch_next_step:                       # step k+1's draws need nothing but the step count
+            draws.prefetch_lambda_and_knots(plan.alpha, step + 1, batch, plan.knot, channels, plan.sigma)
+    else:
+        lam = draws.draw_lambda(plan.alpha, step)
     lam32, one_minus = draws.lambda_pair_fp32(lam)
 
     frames_i32 = host_frames(frames, batch, length)
@@ -112,10 +124,8 @@ def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RE
     uploads = [draws.rand_windows(frames_i32, mix_indices, step, length) if plan.rand_displacement else frames_i32,
                mix_indices.astype(np.int32),
                draws.processing_order(mix_indices) if use_processing_order else np.zeros(0, np.int32)]
-    if plan.branch == "durmixmagwarp":
-        if plan.knot > native.MAX_KNOT:
-            raise ValueError(f"durmixmagwarp knot={plan.knot} exceeds the supported maximum {native.MAX_KNOT}")
-        uploads.append(draws.draw_knots(batch, plan.knot, channels, plan.sigma))
+    if knots is not None:
+        uploads.append(knots)
     on_dev = staging.upload(uploads, data.device)
     knots_dev = on_dev[3] if plan.branch == "durmixmagwarp" else None
     data_new = pcgmix_on_device(data, None if plan.rand_displacement else on_dev[0], on_dev[1], lam32, one_minus,

@@ -192,6 +192,79 @@ def draw_lambda(alpha: float, step: int) -> float:
     return 1.0
 
 
+# The reference leaves NumPy's GLOBAL legacy stream re-seeded and advanced past the lambda (and knot) draws
+# after every step; code that runs later in the same process sees that state.  The C++ replay does not touch
+# NumPy, so the state it ends in is written back (np.random.set_state, ~30 us).  Callers that own every use
+# of np.random in their process may switch the mirroring off.
+mirror_numpy_global_state = True
+
+
+class _Prefetch:
+    """Lambda + knots of one future step, computed on a worker thread (the C++ replay releases the GIL)."""
+    __slots__ = ("key", "future")
+
+
+_prefetch_pool = None
+_prefetched = {}
+_PREFETCH_DEPTH = 8
+
+
+def _replay_key(alpha, sigma, step, shape):
+    return (float(alpha), float(sigma), int(step), tuple(int(d) for d in shape))
+
+
+def _replay(alpha, sigma, step, shape):
+    from . import native
+    return native.host_lambda_knots(step, alpha, sigma, shape, max_threads=1, want_state=mirror_numpy_global_state)
+
+
+def prefetch_lambda_and_knots(alpha: float, step: int, batch: int, knot: int, channels: int, sigma: float) -> None:
+    """Start computing ``lambda_and_knots(...)`` for a future ``step`` in the background.  The seed is the
+    step count (train_model.py:105-109, :577), so step k+1's label-independent draws are known while step k
+    runs; ``lambda_and_knots`` picks the result up (or computes it itself if nobody asked)."""
+    global _prefetch_pool
+    if not (alpha > 0.0 and isinstance(step, (int, np.integer)) and 0 <= step < 2 ** 32):
+        return
+    key = _replay_key(alpha, sigma, step, (batch, knot + 2, channels))
+    if key in _prefetched:
+        return
+    if _prefetch_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _prefetch_pool = ThreadPoolExecutor(max_workers=4, thread_name_prefix="pcgmix-draws")
+    while len(_prefetched) >= _PREFETCH_DEPTH:                 # forget the oldest request nobody collected
+        _prefetched.pop(next(iter(_prefetched)))
+    _prefetched[key] = _prefetch_pool.submit(_replay, alpha, sigma, int(step), key[3])
+
+
+def lambda_and_knots(alpha: float, step: int, batch: int, knot: int, channels: int, sigma: float):
+    """``(lam, knots)`` exactly as the reference draws them (augmentations.py:659-666 then :677):
+    ``np.random.seed(step); lam = np.random.beta(alpha, alpha)`` followed by
+    ``knots = np.random.normal(1.0, sigma, (B, knot+2, C))`` from the same global stream.
+
+    Computed by the C++ replay of NumPy's legacy stream (bit-equal, ~3x faster, no GIL, prefetchable);
+    NumPy itself is used when the replay does not apply: ``alpha <= 0`` (the reference then neither
+    re-seeds nor draws lambda, the knots continue the global stream wherever it stands), seeds NumPy
+    refuses, or a missing library (host logic only: the GPU kernels have no such fallback)."""
+    shape = (int(batch), int(knot) + 2, int(channels))
+    if alpha > 0.0 and isinstance(step, (int, np.integer)) and 0 <= step < 2 ** 32:
+        future = _prefetched.pop(_replay_key(alpha, sigma, step, shape), None)
+        try:
+            lam, knots, state = future.result() if future is not None else _replay(alpha, sigma, int(step), shape)
+        except (ImportError, OSError, RuntimeError):
+            state = None
+        else:
+            if mirror_numpy_global_state:
+                if state is None:                           # prefetched while mirroring was off
+                    np.random.seed(step)
+                    np.random.beta(alpha, alpha)
+                    np.random.normal(loc=1.0, scale=sigma, size=shape)
+                else:
+                    np.random.set_state(state)
+            return lam, knots
+    lam = draw_lambda(alpha, step)
+    return lam, draw_knots(batch, knot, channels, sigma)
+
+
 def lambda_pair_fp32(lam: float):
     """``(lam32, 1 - lam32)`` rounded the way the reference's float32 tensor expression rounds."""
     lam32 = np.array(np.ones(1) * lam).astype("float32")[0]
@@ -247,7 +320,16 @@ def processing_order(mix: np.ndarray) -> np.ndarray:
     """Order in which the device visits the cycles: follow the pairing permutation's chains
     (b, mix[b], mix[mix[b]], ...), so that a cycle is read as "partner" and as "itself" by CTAs
     that are in flight together and the second read is served by L2 instead of HBM.  Any
-    permutation gives the same output; this one only changes locality."""
+    permutation gives the same output; this one only changes locality.  Computed by the native
+    library (20 us per 4096 cycles); the Python loop below is the same walk."""
+    try:
+        from . import native
+        return native.host_processing_order(mix)
+    except (ImportError, OSError, RuntimeError):
+        return _processing_order_python(mix)
+
+
+def _processing_order_python(mix: np.ndarray) -> np.ndarray:
     mix = np.asarray(mix, dtype=np.int64)
     n = mix.shape[0]
     seen = np.zeros(n, dtype=bool)

@@ -52,6 +52,9 @@ SIGNATURES = {
                               _ptr, _ptr, _ptr, _c_i32, _ptr, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_copy_small": [_ptr, _ptr, ctypes.c_int64, _ptr],
     "pcgmix_host_group_permutation": [_ptr, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, _ptr],
+    "pcgmix_host_lambda_knots": [ctypes.c_uint64, ctypes.c_double, ctypes.c_double, ctypes.c_int64, _c_i32,
+                                 _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
+    "pcgmix_host_processing_order": [_ptr, ctypes.c_int64, _ptr],
 }
 
 _lib = None
@@ -200,6 +203,39 @@ def host_group_permutation(group_ids, n_groups: int, seed: int):
     if rc != 0:
         raise RuntimeError("pcgmix_host_group_permutation: bad arguments")
     return mix
+
+
+def host_lambda_knots(seed: int, alpha: float, sigma: float, shape, max_threads: int = 4, want_state: bool = True):
+    """``np.random.seed(seed); lam = beta(alpha, alpha); knots = normal(1, sigma, shape)`` replayed in C++
+    (bit-equal to NumPy's legacy stream).  Returns ``(lam, knots, state)``; ``state`` is the tuple
+    ``np.random.set_state`` accepts (the stream position NumPy would be left at) or None.  Raises
+    ``ValueError`` where the replay does not apply (seed outside [0, 2^32), alpha <= 0)."""
+    import numpy as np
+    n = 1
+    for d in shape:
+        n *= int(d)
+    knots = np.empty(shape, dtype=np.float64)
+    lam = ctypes.c_double()
+    key = np.empty(624, dtype=np.uint32) if want_state else None
+    pos, has_gauss, gauss = _c_i32(), _c_i32(), ctypes.c_double()
+    if not (0 <= int(seed) < 2 ** 32):
+        raise ValueError("seed outside [0, 2^32)")
+    rc = load().pcgmix_host_lambda_knots(int(seed), float(alpha), float(sigma), n, int(max_threads), ctypes.byref(lam),
+                                         knots.ctypes.data, key.ctypes.data if want_state else None, ctypes.byref(pos),
+                                         ctypes.byref(has_gauss), ctypes.byref(gauss))
+    if rc != 0:
+        raise ValueError("pcgmix_host_lambda_knots: the replay does not apply to these arguments")
+    state = ("MT19937", key, pos.value, has_gauss.value, gauss.value) if want_state else None
+    return lam.value, knots, state
+
+
+def host_processing_order(mix):
+    import numpy as np
+    m = np.ascontiguousarray(mix, dtype=np.int64)
+    order = np.empty(m.shape[0], dtype=np.int32)
+    if load().pcgmix_host_processing_order(m.ctypes.data, m.shape[0], order.ctypes.data) != 0:
+        raise RuntimeError("pcgmix_host_processing_order: bad arguments")
+    return order
 
 
 def version() -> int:

@@ -140,14 +140,16 @@ def augment(args, resident: ResidentCycles, cycle_ids, target_ohe, wav, step_cou
     if labels.shape[0] != batch:
         raise ValueError(f"{batch} cycle ids but {labels.shape[0]} targets")
     mix_indices = draws.pairing(args.method, labels, wav, step)
-    lam = draws.draw_lambda(plan.alpha, step)
-    lam32, one_minus = draws.lambda_pair_fp32(lam)
-
     uploads = [mix_indices.astype(np.int32)]
     if plan.branch == "durmixmagwarp":
         if plan.knot > native.MAX_KNOT:
             raise ValueError(f"durmixmagwarp knot={plan.knot} exceeds the supported maximum {native.MAX_KNOT}")
-        uploads.append(draws.draw_knots(batch, plan.knot, resident.channels, plan.sigma))
+        lam, knots = draws.lambda_and_knots(plan.alpha, step, batch, plan.knot, resident.channels, plan.sigma)
+        draws.prefetch_lambda_and_knots(plan.alpha, step + 1, batch, plan.knot, resident.channels, plan.sigma)
+        uploads.append(knots)
+    else:
+        lam = draws.draw_lambda(plan.alpha, step)
+    lam32, one_minus = draws.lambda_pair_fp32(lam)
     if sel_host is not None:
         if not np.issubdtype(sel_host.dtype, np.integer):
             raise TypeError(f"cycle ids must be integers, got {sel_host.dtype}")

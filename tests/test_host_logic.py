@@ -269,3 +269,74 @@ def test_host_frames_accepts_offsets_beyond_the_row_and_rejects_disorder():
             _common.host_frames(torch.tensor(bad), 1, 50)
     with pytest.raises(TypeError):
         _common.host_frames(torch.tensor([[0.0, 1, 2, 3, 4]]), 1, 50)
+
+
+@pytest.mark.parametrize("alpha", [1.0, 0.5, 2.0, 0.3, 7.5])
+def test_lambda_and_knots_replay_is_numpy_bit_for_bit(alpha):
+    """The C++ replay of NumPy's legacy stream (seed -> beta -> normal) against NumPy itself: values, and the
+    state the GLOBAL stream is left in (the reference re-seeds it every step; later code sees that)."""
+    for step in list(range(120)) + [2 ** 32 - 1, 3_000_000_019 % 2 ** 32]:
+        for shape in ((5, 6, 4), (1, 2, 1), (33, 9, 3)):
+            np.random.seed(step)
+            lam = np.random.beta(alpha, alpha)
+            knots = np.random.normal(loc=1.0, scale=0.2, size=shape)
+            after = np.random.random_sample(3)
+            np.random.seed(12345)
+            got_lam, got_knots = draws.lambda_and_knots(alpha, step, shape[0], shape[1] - 2, shape[2], 0.2)
+            assert got_lam == lam and np.array_equal(got_knots, knots), (alpha, step, shape)
+            assert np.array_equal(np.random.random_sample(3), after), "global NumPy stream not left where the reference leaves it"
+
+
+def test_lambda_and_knots_prefetch_and_fallbacks():
+    np.random.seed(77)
+    lam = np.random.beta(1, 1)
+    knots = np.random.normal(1.0, 0.2, (64, 6, 4))
+    draws.prefetch_lambda_and_knots(1, 77, 64, 4, 4, 0.2)
+    draws.prefetch_lambda_and_knots(1, 77, 64, 4, 4, 0.2)            # asking twice is harmless
+    got = draws.lambda_and_knots(1, 77, 64, 4, 4, 0.2)
+    assert got[0] == lam and np.array_equal(got[1], knots)
+    # more requests than the pool keeps: the oldest are dropped, results stay right
+    for k in range(20):
+        draws.prefetch_lambda_and_knots(1, 1000 + k, 8, 4, 2, 0.2)
+    np.random.seed(1003)
+    lam = np.random.beta(1, 1)
+    knots = np.random.normal(1.0, 0.2, (8, 6, 2))
+    got = draws.lambda_and_knots(1, 1003, 8, 4, 2, 0.2)
+    assert got[0] == lam and np.array_equal(got[1], knots)
+    # alpha <= 0: no re-seed, lambda 1, knots continue the global stream wherever it stands
+    np.random.seed(5)
+    np.random.random_sample(7)
+    state = np.random.get_state()
+    want = np.random.normal(1.0, 0.3, (4, 6, 2))
+    np.random.set_state(state)
+    lam0, knots0 = draws.lambda_and_knots(0.0, 9, 4, 4, 2, 0.3)
+    assert lam0 == 1.0 and np.array_equal(knots0, want)
+    # mirroring switched off: values unchanged, global stream untouched
+    draws.mirror_numpy_global_state = False
+    try:
+        np.random.seed(31)
+        probe = np.random.get_state()[1].copy()
+        draws.lambda_and_knots(1, 8, 4, 4, 2, 0.2)
+        assert np.array_equal(np.random.get_state()[1], probe)
+    finally:
+        draws.mirror_numpy_global_state = True
+
+
+def test_processing_order_native_equals_python_walk():
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 2, 17, 4096):
+        mix = rng.permutation(n)
+        assert np.array_equal(draws.processing_order(mix), draws._processing_order_python(mix))
+    mix = np.array([1, 0, 7, 2])                                     # an entry outside the batch ends its chain
+    assert np.array_equal(draws.processing_order(mix), draws._processing_order_python(mix))
+
+
+def test_host_labels_side_channel():
+    from pcgmix_b200 import _common
+    target = torch.tensor([0, 1, 1, 0, 1])
+    ohe = torch.nn.functional.one_hot(target, 2)
+    assert np.array_equal(_common.labels_from_one_hot(ohe), [0, 1, 1, 0, 1])
+    tagged = _common.with_host_labels(ohe, target)
+    assert tagged is ohe and np.array_equal(_common.labels_from_one_hot(ohe), [0, 1, 1, 0, 1])
+    with pytest.raises(ValueError):
+        _common.with_host_labels(ohe, torch.tensor([0, 1]))
