@@ -32,7 +32,10 @@ def main():
     b = 64
     frames = synth.cycle_frames(rng, b, limit=2500)
     data = torch.from_numpy(synth.cycle_signals(rng, frames, (4,), 2500)).to(dev)
-    ohe = torch.nn.functional.one_hot(torch.from_numpy(rng.integers(0, 2, b)), 2).to(dev)
+    target = torch.from_numpy(rng.integers(0, 2, b))
+    ohe = torch.nn.functional.one_hot(target, 2).to(dev)
+    if "--host-labels" in sys.argv:                      # the loader's CPU target handed over: no device read-back
+        augmentations.with_host_labels(ohe, target)
     ft = torch.from_numpy(frames)
     wav = ["a"] * b
     step = Step()

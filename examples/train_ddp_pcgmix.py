@@ -88,6 +88,9 @@ def main():
     ap.add_argument("--resident", action="store_true",
                     help="keep the rank's recordings + cycle table on the GPU and draw batches as table rows "
                          "(pcgmix_b200.resident): no per-step upload, no padded array")
+    ap.add_argument("--device-labels", action="store_true",
+                    help="recover the class ids from the device one-hot tensor every step, like the reference "
+                         "(augmentations.py:501), instead of taking them from the loader's CPU target")
     opt = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -132,6 +135,8 @@ def main():
         if not opt.resident:
             data = host_data.to(dev, non_blocking=True)            # train_model.py:499
         target_ohe = F.one_hot(target, args.num_classes).to(dev)
+        if not opt.device_labels:                              # the loader's CPU target: pairing needs no device read-back
+            augmentations.with_host_labels(target_ohe, target)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         h0 = time.perf_counter()

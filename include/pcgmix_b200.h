@@ -48,14 +48,18 @@
 extern "C" {
 #endif
 
-#define PCGMIX_B200_VERSION 101
+#define PCGMIX_B200_VERSION 102
 
 /* bits OR-ed into *err_flag (device int32, may be NULL) by the kernels */
 #define PCGMIX_ERR_BAD_PARTNER   1   /* mix[b] outside [0,B): cycle copied unmixed          */
-#define PCGMIX_ERR_BAD_FRAMES    2   /* frames not monotone / outside [0,P]: state skipped    */
+#define PCGMIX_ERR_BAD_FRAMES    2   /* offsets negative / decreasing, or a pair's clamped windows
+                                        differ in width (the reference raises): cycle copied  */
 #define PCGMIX_ERR_BAD_PATTERN   4   /* S1 followed by something other than sys,S2,dia        */
 #define PCGMIX_ERR_OVERFLOW      8   /* more cycles/transitions than the output can hold      */
 #define PCGMIX_ERR_ZERO_DIVISION 16  /* duration ratio with a zero denominator                */
+#define PCGMIX_ERR_EMPTY_STATE   32  /* a heart state without samples: features are NaN       */
+
+#define PCGMIX_CYCLE_FEATURES 36     /* floats per cycle written by pcgmix_cycle_features       */
 
 #define PCGMIX_MAX_KNOT 30           /* largest `knot` of durmixmagwarp(sigma,knot) supported */
 
@@ -97,11 +101,16 @@ int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, i
  * When enabled, a pipelined launch whose buffers are disjoint from those of the previous two PCGmix
  * launches on the same stream (checked here: no read-after-write, write-after-read or
  * write-after-write overlap) is issued with the programmatic-stream-serialization attribute, and
- * every pipelined kernel signals `griddepcontrol.launch_dependents` when its CTAs start their last
- * slice: the next launch fills its pipeline while the previous one drains (measured: 12-14 us per
- * launch at 4096 cycles).  By enabling it the caller asserts that no OTHER kernel enqueued on that
- * stream between two PCGmix launches produces or consumes these buffers while signalling early
- * completion itself (ordinary kernels and copies never do).  Results are unchanged.
+ * every pipelined kernel signals `griddepcontrol.launch_dependents` as soon as its CTAs are running:
+ * the next launch's CTAs take over SMs as this one's retire, so its pipeline fills while the previous
+ * one drains (measured: 12-14 us per launch at 4096 cycles).  Only grids that fill the GPU exactly (CTA
+ * residency as counted by the runtime's occupancy calculator) with identical geometry are overlapped,
+ * so at most two are in flight.  Every OTHER entry point of this library that launches on the stream
+ * (pcgmix_copy_small, the segmentation / cut / feature kernels, pcgmix_mix1d_resident) resets the
+ * bookkeeping, so a mix launch is never made a programmatic dependent of the kernel that produced its
+ * tables.  The library cannot see kernels of OTHER libraries: by enabling overlap the caller asserts
+ * that nothing it enqueues itself between two PCGmix launches on that stream writes their inputs or
+ * reads their outputs.  Results are unchanged.
  */
 int pcgmix_set_launch_overlap(int32_t enable);
 /* Number of launches issued so far with the overlap attribute (diagnostics). */
@@ -121,6 +130,11 @@ long long pcgmix_overlap_launches(void);
  * out[b,c,t] = x[b,c,t]*lam + x[mix[b],c,f2[s]+(t-f1[s])]*one_minus_lam for t inside the
  * first min(len1_s,len2_s) samples of state s, else x[b,c,t]; mul, mul, add each rounded
  * to fp32 (no FMA contraction), exactly like the reference's tensor expression.
+ * Offsets may exceed L (the reference keeps cycles longer than the padded row): both windows are
+ * clamped to the row like the reference's Python slices and blended when the clamped widths agree;
+ * otherwise the reference raises a shape mismatch and this kernel copies the cycle and raises
+ * PCGMIX_ERR_BAD_FRAMES.  Entries of `order` and `mix` outside [0,B) are not followed
+ * (PCGMIX_ERR_BAD_PARTNER).
  */
 int pcgmix_mix1d(const float* x, float* out, const int32_t* frames, int32_t frame_stride,
                  const int32_t* mix, const int32_t* order, float lam, float one_minus_lam,
@@ -230,6 +244,27 @@ int pcgmix_mix1d_resident(const float* signal, int32_t n_rec, int32_t C, int32_t
                           float* out, int32_t B, int32_t L, int32_t* scratch, int32_t* err_flag,
                           pcgmix_stream_t stream);
 
+/*
+ * Classical per-cycle features of one channel of a batch of (augmented) cycles: what
+ * classical.feature_vector_seg computes in its amplitude block (classical.py:284-303) and its Hilbert
+ * envelope block (:305-360), for the loop at train_model.py:519-532.  x [B][C][L] fp32, frames as for
+ * pcgmix_mix1d, `channel` the row of every cycle to use (the reference passes d[4]), `what` a mask:
+ * 1 = amplitude block, 2 = envelope block.  features [B][PCGMIX_CYCLE_FEATURES] fp32:
+ *    0..3   max amplitude of S1, systole, S2, diastole
+ *    4..9   round(.,4) of max ratios S1/S2, sys/dia, sys/S1, sys/S2, dia/S1, dia/S2
+ *   10..14  envelope integral (np.trapz, dx=5) of S1, systole, S2, diastole, RR
+ *   15..22  round(.,4) of integral ratios S1/S2, sys/dia, S1/RR, sys/RR, S2/RR, dia/RR, sys/S1, dia/S2
+ *   23..27  mean envelope of S1, systole, S2, diastole, RR
+ *   28..35  mean-envelope ratios S1/RR, sys/RR, S2/RR, dia/RR, sys/dia, sys/S1, dia/S2, S1/S2
+ * Segments are the reference's slices (S1 = data[:f1], RR = data[:f4], bounds clamped to L).  The amplitude
+ * block is exact (float32, NumPy's round); the envelope block agrees with SciPy's single-precision FFT
+ * to float32 rounding.  Blocks not requested are left untouched.  A cycle with an empty state gets NaN
+ * features and raises PCGMIX_ERR_EMPTY_STATE (the reference raises).  L <= 14000 for the envelope block.
+ */
+int pcgmix_cycle_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
+                          int32_t L, int32_t channel, int32_t what, float* features, int32_t* err_flag,
+                          pcgmix_stream_t stream);
+
 /* 14 fp64 features per cycle from frames [n][5] int32 (stride `frame_stride` int32 between rows). */
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,
                              double* features, int32_t* err_flag, pcgmix_stream_t stream);
@@ -272,6 +307,22 @@ int pcgmix_host_lambda_knots(uint64_t seed, double alpha, double sigma, int64_t 
  * processing order that keeps a cycle read as "partner" in L2 until it is read as "itself".  Host code.
  */
 int pcgmix_host_processing_order(const int64_t* mix, int64_t n, int32_t* order);
+
+/*
+ * The integer half of the host's share of one plain PCGmix / PCGmix+ step in a single call (no Python in between):
+ * the reference's get_same_label_mix_indices (augmentations.py:500-514) plus the offset checks of this
+ * implementation, packed into a staging buffer that pcgmix_copy_small uploads verbatim.  labels[B]: class id per
+ * cycle; frames: CPU offsets, row b at frames + b*frame_stride (int64), 5 per row; L: row length; seed: the step
+ * count; K >= 0: reserve a section for (B, K+2, C) float64 knots (the caller fills it); want_order: also write the
+ * pairing-chain processing order.  info[0..3]: byte offsets in `packed` of {frames int32 [B][5], mix int32 [B],
+ * order int32 [B], knots} (-1 = absent), info[4]: bytes used; mix_out[B]: the pairing as int64.  info holds 16 entries.
+ * Returns 0, or: 1 bad arguments / buffer too small (info[4] = bytes needed); 2 offsets of cycle info[5] negative,
+ * decreasing or beyond int32; 3 cycle info[5], state info[6]: clamped destination / source windows of
+ * info[7] / info[8] samples (the reference raises a shape mismatch there).
+ */
+int pcgmix_host_prepare_step(const int64_t* labels, int64_t B, const int64_t* frames, int64_t frame_stride, int64_t L,
+                             uint64_t seed, int32_t K, int32_t C, int32_t want_order, uint8_t* packed, int64_t capacity,
+                             int64_t* info, int64_t* mix_out);
 
 #ifdef __cplusplus
 }

@@ -90,21 +90,107 @@ def prepare_on_device(data, frames_dev, mix_dev, lam32, one_minus_lam32, out, kn
                                 knot, order=order_dev, err_flag=err_flag)
 
 
+_plans = {}
+
+
+def _plan_for(method: str):
+    """``draws.parse_method_1d`` with the result remembered per method string (a training run calls
+    ``augment`` with the same string every step; ``None`` and refusals are not cached)."""
+    plan = _plans.get(method)
+    if plan is None:
+        plan = draws.parse_method_1d(method)
+        if plan is not None:
+            if len(_plans) > 64:
+                _plans.clear()
+            _plans[method] = plan
+    return plan
+
+
+# below this many knot ordinates per step NumPy itself draws them (a C call either way, and NumPy then leaves
+# its global stream where the reference leaves it without a 30 us set_state)
+_SMALL_DRAW = 16384
+
+
+def _plain_step(plan, data, target_ohe, frames, step):
+    """The common case — default same-label pairing, no ``(rand)`` / ``(mixAll)`` / name-based modifiers — with
+    the host's integer work done by ONE native call straight into the pinned staging buffer
+    (``pcgmix_host_prepare_step``) and the tables handed to the kernel as offsets into one device buffer.
+    Returns ``(data_new, mix_indices)`` or ``None`` if this path does not apply (the general path then runs)."""
+    batch, channels, length = data.shape
+    magwarp = plan.branch == "durmixmagwarp"
+    if not isinstance(frames, torch.Tensor) or frames.is_cuda or frames.dim() != 2 or frames.shape[0] != batch \
+            or frames.shape[1] < 5 or not isinstance(step, (int, np.integer)) or not 0 <= step < 2 ** 32 \
+            or not plan.alpha > 0.0:
+        return None
+    if magwarp and plan.knot > native.MAX_KNOT:
+        raise ValueError(f"durmixmagwarp knot={plan.knot} exceeds the supported maximum {native.MAX_KNOT}")
+    if frames.dtype != torch.int64:
+        if frames.dtype.is_floating_point or frames.dtype == torch.bool:
+            raise TypeError(f"frames must hold integers, got {frames.dtype}")
+        frames = frames.to(torch.int64)
+    f_np = frames.numpy()
+    if f_np.strides[1] != 8 or f_np.strides[0] % 8 or f_np.strides[0] < 40:
+        f_np = np.ascontiguousarray(f_np)
+    labels = np.ascontiguousarray(labels_from_one_hot(target_ohe), dtype=np.int64)
+    knot = plan.knot if magwarp else -1
+    n_knots = batch * (plan.knot + 2) * channels if magwarp else 0
+    slot = staging.reserve(data.device, batch * 28 + n_knots * 8 + 64)
+    rc, info, mix_indices = native.host_prepare_step(labels, f_np, length, step, knot, channels, use_processing_order, slot.buf)
+    if rc == 2:
+        bad = int(info[5])
+        raise ValueError(f"frames[{bad}] = {f_np[bad, :5].tolist()} is not a non-negative, non-decreasing int32 offset list")
+    if rc == 3:
+        b, s_, wd, ws = (int(v) for v in info[5:9])
+        raise RuntimeError(
+            f"cycle {b} (offsets {f_np[b, :5].tolist()}) cannot be blended with its partner {int(mix_indices[b])} "
+            f"(offsets {f_np[int(mix_indices[b]), :5].tolist()}) in a row of {length} samples: state {s_} clamps to "
+            f"{wd} destination and {ws} source samples (the reference raises a shape mismatch here)")
+    if rc != 0:
+        return None
+    # lambda (and knots) from NumPy's legacy global stream, as the reference draws them
+    if magwarp:
+        if n_knots <= _SMALL_DRAW:
+            lam = draws.draw_lambda(plan.alpha, step)
+            knots = draws.draw_knots(batch, plan.knot, channels, plan.sigma)
+        else:
+            lam, knots = draws.lambda_and_knots(plan.alpha, step, batch, plan.knot, channels, plan.sigma)
+            if prefetch_next_step:                   # step k+1's draws need nothing but the step count
+                draws.prefetch_lambda_and_knots(plan.alpha, step + 1, batch, plan.knot, channels, plan.sigma)
+        off = int(info[3])
+        slot.buf.numpy()[off:off + n_knots * 8] = knots.reshape(-1).view(np.uint8)
+    else:
+        lam = draws.draw_lambda(plan.alpha, step)
+    lam32, one_minus = draws.lambda_pair_fp32(lam)
+    tables = staging.commit(slot, int(info[4]), data.device)
+    data_new = torch.empty_like(data)
+    if magwarp:
+        pos_dev, mat_dev = _device_tables(length, plan.knot, data.device)
+        native.mix1d_packed(data, data_new, tables, info, lam32, one_minus, mat_dev, pos_dev, plan.knot)
+    else:
+        native.mix1d_packed(data, data_new, tables, info, lam32, one_minus)
+    return data_new, mix_indices
+
+
 def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RESULTS_ARGS):
     """PCGmix (``durratiomixup``) / PCGmix+ (``durmixmagwarp(sigma,knot)``) on a (B, C, L) batch.
 
     Returns ``(data_new, target_ohe, mix_indices, None)``; when the method is not one the
     reference implements, or the probability gate fails, returns ``(data, target_ohe, [], None)``
     with the very same objects (``augmentations.py:731-732, 938-939``)."""
-    plan = draws.parse_method_1d(args.method)
+    plan = _plan_for(args.method)
     if plan is None:
         return data, target_ohe, [], None
     step = step_counter.count
-    if draws.gate(step) >= plan.probability:
+    # (the gate variate lies in [0, 1): with probability 1 the draw cannot fail and has no other effect)
+    if plan.probability < 1.0 and draws.gate(step) >= plan.probability:
         return data, target_ohe, [], None
 
     data = require_cuda_batch(data, 3, "augment")
     batch, channels, length = data.shape
+    if not (plan.rand_displacement or plan.mix_all or "(samePCG)" in args.method or "(sameDataset)" in args.method):
+        done = _plain_step(plan, data, target_ohe, frames, step)
+        if done is not None:
+            return done[0], target_ohe, done[1], None
     labels = labels_from_one_hot(target_ohe)
     mix_indices = draws.pairing(args.method, labels, wav, step)
     knots = None
@@ -112,8 +198,6 @@ def augment(args, data, target_ohe, frames, wav, step_counter, model, device, RE
         if plan.knot > native.MAX_KNOT:
             raise ValueError(f"durmixmagwarp knot={plan.knot} exceeds the supported maximum {native.MAX_KNOT}")
         lam, knots = draws.lambda_and_knots(plan.alpha, step, batch, plan.knot, channels, plan.sigma)
-        if prefetch_next_step:                       # step k+1's draws need nothing but the step count
-            draws.prefetch_lambda_and_knots(plan.alpha, step + 1, batch, plan.knot, channels, plan.sigma)
     else:
         lam = draws.draw_lambda(plan.alpha, step)
     lam32, one_minus = draws.lambda_pair_fp32(lam)

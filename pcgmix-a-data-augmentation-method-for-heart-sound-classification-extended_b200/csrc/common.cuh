@@ -127,6 +127,10 @@ cudaError_t launch_segment_table(const int32_t* positions, const int8_t* codes, 
 cudaError_t launch_cut_cycles(const float* signal, int32_t R, int32_t C, int32_t T, const int32_t* cycles,
                               int32_t n_cycles, const int32_t* n_cycles_dev, float* out, int32_t L,
                               cudaStream_t stream);
+// feature_kernels.cu
+cudaError_t launch_cycle_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
+                                  int32_t L, int32_t channel, int32_t what, float* features, int32_t* err,
+                                  cudaStream_t stream);
 cudaError_t launch_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,
                                      double* features, int32_t* err, cudaStream_t stream);
 

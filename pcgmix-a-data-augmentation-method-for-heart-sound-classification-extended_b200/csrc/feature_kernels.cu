@@ -1,0 +1,259 @@
+// Per-cycle classical features of (augmented) cycles, computed where the cycles already are (sm_100a).
+//
+// What it replaces (reference = PCGmix-EXTENDED): with `args.classical_space` the training loop takes every
+// augmented batch back to the host and runs `classical.feature_vector_seg` on one channel of every cycle in a
+// Python loop, concatenating pandas columns (train_model.py:519-532).  The per-cycle arithmetic of that
+// function's first blocks is a handful of segmented reductions over the four heart states:
+//
+//   amplitude block (classical.py:284-303)   np.max per state, six ratios round(a/b, 4)
+//   envelope block  (classical.py:305-360)   |hilbert(segment)| for S1, systole, S2, diastole and the whole
+//                                            beat; np.trapz(dx=5) integrals, eight rounded integral ratios,
+//                                            five means, eight mean ratios
+//
+// (the duration block, :248-283, is pcgmix_duration_features in segment_kernels.cu; the Welch / wavelet /
+// entropy blocks that follow are not provided).
+//
+// Numerics.  The reference works on float32 cycles, so every quantity above is float32 there.  Amplitude block:
+// exact — a maximum is a selection, NaN propagates like np.max, and NumPy's round(x, 4) on a float32 scalar is
+// rint(x * 1e4f) / 1e4f in float32, reproduced with __fmul_rn / rintf / __fdiv_rn.  Envelope block: SciPy takes a
+// single-precision FFT of each segment (arbitrary length), zeroes the negative frequencies and transforms back;
+// the imaginary part of that analytic signal is the circular convolution of the segment with the discrete
+// Hilbert kernel
+//     N even:  h[m] = (2/N) cot(pi m / N) for odd m, 0 for even m
+//     N odd :  h[m] = (1/N) (cos(pi m / N) - (-1)^m) / sin(pi m / N)
+// which is evaluated here directly (O(N^2) FMAs per segment out of shared memory: 1.7 M per cycle, nothing next
+// to the batch's HBM traffic).  Both are float32 computations of the same quantity with different rounding
+// orders, so parity is a tolerance (tests: 2e-5 relative on integrals and means, one unit of the fourth
+// decimal on the rounded ratios), not bit equality.
+//
+// Segments follow the reference's slices exactly: S1 = data[:f1] (from column 0, not from f0), systole =
+// data[f1:f2], S2 = data[f2:f3], diastole = data[f3:f4], RR = data[:f4], every bound clamped to the row length
+// like a Python slice.  An empty segment makes the reference raise (np.max of nothing); here the cycle's
+// features are NaN and PCGMIX_ERR_EMPTY_STATE is raised.
+
+#include "common.cuh"
+
+namespace pcgmix {
+
+namespace {
+
+constexpr int kFeatThreads = 256;
+constexpr int kTile = 4;               // envelope outputs per thread and pass
+
+__device__ __forceinline__ float round4(float v) {      // NumPy's round(float32, 4)
+    return __fdiv_rn(rintf(__fmul_rn(v, 10000.0f)), 10000.0f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+
+// sum over the CTA; every thread gets the result (two barriers)
+__device__ __forceinline__ float block_sum(float v, float* scratch) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = threadIdx.x < kFeatThreads / 32 ? scratch[threadIdx.x] : 0.0f;
+    if (threadIdx.x < 32) {
+        t = warp_sum(t);
+        if (threadIdx.x == 0) scratch[kFeatThreads / 32] = t;
+    }
+    __syncthreads();
+    const float r = scratch[kFeatThreads / 32];
+    __syncthreads();
+    return r;
+}
+
+struct FeatArgs {
+    const float* x;
+    const int32_t* frames;
+    int32_t frame_stride;
+    int32_t B, C, L, channel;
+    float* features;
+    int32_t* err;
+    int32_t what;              // bit 0: amplitude block, bit 1: envelope block
+};
+
+__global__ void __launch_bounds__(kFeatThreads) cycle_features_kernel(const __grid_constant__ FeatArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ float s_red[kFeatThreads / 32 + 1];
+    __shared__ float s_max[4][kFeatThreads / 32];
+    __shared__ int s_nan[4];
+    const int b = blockIdx.x;
+    const float* __restrict__ row = a.x + (static_cast<size_t>(b) * a.C + a.channel) * a.L;
+    float* __restrict__ out = a.features + static_cast<size_t>(b) * PCGMIX_CYCLE_FEATURES;
+    int c[5];
+    bool sane = true;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) {
+        const int f = __ldg(a.frames + static_cast<size_t>(b) * a.frame_stride + s);
+        sane = sane && f >= 0;
+        c[s] = min(max(f, 0), a.L);
+    }
+    // the reference's slices: S1 starts at column 0; a bound below its predecessor gives an empty slice
+    const int beg[5] = {0, c[1], c[2], c[3], 0};
+    const int end[5] = {c[1], c[2], c[3], c[4], c[4]};
+    bool empty = !sane;
+#pragma unroll
+    for (int s = 0; s < 5; ++s) empty = empty || end[s] <= beg[s];
+    if (empty) {
+        for (int i = threadIdx.x; i < PCGMIX_CYCLE_FEATURES; i += kFeatThreads) out[i] = __int_as_float(0x7fc00000);
+        if (threadIdx.x == 0 && a.err != nullptr) atomicOr(a.err, static_cast<int>(PCGMIX_ERR_EMPTY_STATE));
+        return;
+    }
+
+    if (a.what & 1) {
+        // ---- amplitude block: per-state maximum (NaN propagates), six rounded ratios ------------------------
+        if (threadIdx.x < 4) s_nan[threadIdx.x] = 0;
+        __syncthreads();
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        bool nan[4] = {false, false, false, false};
+        for (int t = threadIdx.x; t < c[4]; t += kFeatThreads) {
+            const float v = __ldg(row + t);
+            const int s = (t >= c[1]) + (t >= c[2]) + (t >= c[3]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (s == k) {
+                    mx[k] = fmaxf(mx[k], v);
+                    nan[k] = nan[k] || (v != v);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float m = mx[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFullMask, m, o));
+            if ((threadIdx.x & 31) == 0) s_max[k][threadIdx.x >> 5] = m;
+            if (__any_sync(kFullMask, nan[k]) && (threadIdx.x & 31) == 0) atomicOr(&s_nan[k], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float m[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                m[k] = s_max[k][0];
+                for (int w = 1; w < kFeatThreads / 32; ++w) m[k] = fmaxf(m[k], s_max[k][w]);
+                if (s_nan[k]) m[k] = __int_as_float(0x7fc00000);
+                out[k] = m[k];
+            }
+            out[4] = round4(__fdiv_rn(m[0], m[2]));      // S1 / S2
+            out[5] = round4(__fdiv_rn(m[1], m[3]));      // systole / diastole
+            out[6] = round4(__fdiv_rn(m[1], m[0]));      // systole / S1
+            out[7] = round4(__fdiv_rn(m[1], m[2]));      // systole / S2
+            out[8] = round4(__fdiv_rn(m[3], m[0]));      // diastole / S1
+            out[9] = round4(__fdiv_rn(m[3], m[2]));      // diastole / S2
+        }
+        __syncthreads();
+    }
+
+    if (a.what & 2) {
+        // ---- envelope block ---------------------------------------------------------------------------------
+        // shared memory: xs[2N] (the segment twice, so that (n - m) mod N is a plain offset), hs[N] (Hilbert
+        // kernel), es[N] (envelope); N <= c[4] <= L
+        const int cap = c[4];
+        float* xs = smem;
+        float* hs = xs + 2 * cap;
+        float* es = hs + cap;
+        float integral[5], mean[5];
+#pragma unroll 1
+        for (int s = 0; s < 5; ++s) {
+            const int n0 = beg[s];
+            const int N = end[s] - n0;
+            for (int t = threadIdx.x; t < N; t += kFeatThreads) {
+                const float v = __ldg(row + n0 + t);
+                xs[t] = v;
+                xs[t + N] = v;
+                float h = 0.0f;
+                if (t > 0) {
+                    float sn, cs;
+                    sincospif(static_cast<float>(t) / static_cast<float>(N), &sn, &cs);
+                    if (N & 1) {
+                        h = (cs - ((t & 1) ? -1.0f : 1.0f)) / (sn * static_cast<float>(N));
+                    } else {
+                        h = (t & 1) ? 2.0f * cs / (sn * static_cast<float>(N)) : 0.0f;
+                    }
+                }
+                hs[t] = h;
+            }
+            __syncthreads();
+            const int m_step = (N & 1) ? 1 : 2;          // even N: only odd taps are non-zero
+            for (int base = threadIdx.x; base < N; base += kFeatThreads * kTile) {
+                float acc[kTile];
+                int idx[kTile];
+#pragma unroll
+                for (int j = 0; j < kTile; ++j) {
+                    acc[j] = 0.0f;
+                    idx[j] = min(base + j * kFeatThreads, N - 1) + N;      // (clamped lanes compute a duplicate, not stored)
+                }
+                for (int m = 1; m < N; m += m_step) {
+                    const float h = hs[m];
+#pragma unroll
+                    for (int j = 0; j < kTile; ++j) acc[j] = fmaf(h, xs[idx[j] - m], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < kTile; ++j) {
+                    const int n = base + j * kFeatThreads;
+                    if (n < N) {
+                        const float re = xs[n];
+                        es[n] = sqrtf(fmaf(re, re, acc[j] * acc[j]));
+                    }
+                }
+            }
+            __syncthreads();
+            float part_int = 0.0f, part_sum = 0.0f;
+            for (int t = threadIdx.x; t < N; t += kFeatThreads) {
+                part_sum += es[t];
+                if (t + 1 < N) part_int += __fmul_rn(5.0f, es[t + 1] + es[t]) * 0.5f;      // np.trapz term, dx = 5
+            }
+            integral[s] = block_sum(part_int, s_red);
+            mean[s] = block_sum(part_sum, s_red) / static_cast<float>(N);
+        }
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                out[10 + s] = integral[s];
+                out[23 + s] = mean[s];
+            }
+            out[15] = round4(__fdiv_rn(integral[0], integral[2]));      // S1 / S2
+            out[16] = round4(__fdiv_rn(integral[1], integral[3]));      // systole / diastole
+            out[17] = round4(__fdiv_rn(integral[0], integral[4]));      // S1 / RR
+            out[18] = round4(__fdiv_rn(integral[1], integral[4]));      // systole / RR
+            out[19] = round4(__fdiv_rn(integral[2], integral[4]));      // S2 / RR
+            out[20] = round4(__fdiv_rn(integral[3], integral[4]));      // diastole / RR
+            out[21] = round4(__fdiv_rn(integral[1], integral[0]));      // systole / S1
+            out[22] = round4(__fdiv_rn(integral[3], integral[2]));      // diastole / S2
+            out[28] = __fdiv_rn(mean[0], mean[4]);                       // S1 / RR
+            out[29] = __fdiv_rn(mean[1], mean[4]);                       // systole / RR
+            out[30] = __fdiv_rn(mean[2], mean[4]);                       // S2 / RR
+            out[31] = __fdiv_rn(mean[3], mean[4]);                       // diastole / RR
+            out[32] = __fdiv_rn(mean[1], mean[3]);                       // systole / diastole
+            out[33] = __fdiv_rn(mean[1], mean[0]);                       // systole / S1
+            out[34] = __fdiv_rn(mean[3], mean[2]);                       // diastole / S2
+            out[35] = __fdiv_rn(mean[0], mean[2]);                       // S1 / S2
+        }
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_cycle_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
+                                  int32_t L, int32_t channel, int32_t what, float* features, int32_t* err,
+                                  cudaStream_t stream) {
+    if (B == 0) return cudaSuccess;
+    FeatArgs a{x, frames, frame_stride, B, C, L, channel, features, err, what};
+    const size_t smem = (what & 2) ? static_cast<size_t>(L) * 4 * sizeof(float) : 0;
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    if (smem > 48 * 1024) {
+        // (per device and cheap: set every time rather than remembered per device)
+        const cudaError_t e = cudaFuncSetAttribute(cycle_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+    }
+    cycle_features_kernel<<<static_cast<unsigned>(B), kFeatThreads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace pcgmix

@@ -338,3 +338,104 @@ extern "C" int pcgmix_host_group_permutation(const int64_t* group, int64_t n, in
     }
     return 0;
 }
+
+
+// The integer half of what the host contributes to one plain PCGmix / PCGmix+ step, in ONE call that never
+// touches Python: offsets checked and narrowed to int32, same-label pairing, the clamped-window check,
+// optional processing order — packed into the caller's (pinned) staging buffer in the layout the upload kernel
+// copies verbatim, with a section reserved for the knots (the caller fills it from pcgmix_host_lambda_knots
+// or from NumPy).  The drop-in augment() spent ~0.3 ms of interpreter time on these pieces at the reference's
+// batch of 64 cycles, for a kernel that runs ~10 us (profiles/README.md).
+//
+//   labels[B]            class id per cycle (arg-max of the one-hot target)
+//   frames               CPU offsets, row b at frames + b*frame_stride (int64 elements), 5 per row
+//   packed / capacity    staging buffer; sections start at 16-byte boundaries
+//   info[0..3]           byte offsets of {frames int32 [B][5], mix int32 [B], order int32 [B], knots f64 [B][K+2][C]}
+//                        (-1: section absent), info[4] total bytes, info[5..8] on status 3: cycle, state,
+//                        clamped destination width, clamped source width; on status 2: info[5] = cycle
+//   mix_out[B]           the pairing as int64 (augment() returns it)
+// Status: 0 ok; 1 bad arguments / buffer too small; 2 offsets negative, decreasing or beyond int32;
+// 3 a pair's clamped windows differ in width (the reference raises a shape mismatch; see pair_window in
+// common.cuh, same rule).
+extern "C" int pcgmix_host_prepare_step(const int64_t* labels, int64_t B, const int64_t* frames, int64_t frame_stride,
+                                        int64_t L, uint64_t seed, int32_t K, int32_t C, int32_t want_order,
+                                        uint8_t* packed, int64_t capacity, int64_t* info, int64_t* mix_out) {
+    if (B < 0 || B >= (1ll << 31) || L <= 0 || frame_stride < 5 || info == nullptr) return 1;
+    if (B > 0 && (labels == nullptr || frames == nullptr || packed == nullptr || mix_out == nullptr)) return 1;
+    if (K >= 0 && C <= 0) return 1;
+    auto align16 = [](int64_t v) { return (v + 15) & ~static_cast<int64_t>(15); };
+    const int64_t n_knots = K >= 0 ? B * (K + 2) * C : 0;
+    const int64_t off_frames = 0;
+    const int64_t off_mix = align16(off_frames + B * 20);
+    const int64_t off_order = want_order ? align16(off_mix + B * 4) : -1;
+    const int64_t off_knots = K >= 0 ? align16((want_order ? off_order : off_mix) + B * 4) : -1;
+    const int64_t total = align16(K >= 0 ? off_knots + n_knots * 8 : (want_order ? off_order : off_mix) + B * 4);
+    info[0] = off_frames; info[1] = off_mix; info[2] = off_order; info[3] = off_knots; info[4] = total;
+    if (total > capacity) return 1;
+
+    // offsets: non-negative, non-decreasing, int32
+    int32_t* f32 = reinterpret_cast<int32_t*>(packed + off_frames);
+    for (int64_t b = 0; b < B; ++b) {
+        const int64_t* f = frames + b * frame_stride;
+        bool ok = f[0] >= 0 && f[4] <= 2147483647ll;
+        for (int s = 0; s < 4; ++s) ok = ok && f[s + 1] >= f[s];
+        if (!ok) {
+            info[5] = b;
+            return 2;
+        }
+        for (int s = 0; s < 5; ++s) f32[b * 5 + s] = static_cast<int32_t>(f[s]);
+    }
+
+    // pairing: a seeded permutation inside every class, each class from a fresh Random(seed)
+    {
+        std::vector<int64_t> keys;                          // distinct class ids in order of first appearance
+        std::vector<std::vector<int64_t>> members;
+        for (int64_t i = 0; i < B; ++i) {
+            size_t g = 0;
+            while (g < keys.size() && keys[g] != labels[i]) ++g;
+            if (g == keys.size()) {
+                if (keys.size() >= 4096) return 1;          // (linear search: meant for a handful of classes)
+                keys.push_back(labels[i]);
+                members.emplace_back();
+            }
+            members[g].push_back(i);
+        }
+        Mt19937 seeded, rng;
+        seeded.seed(seed);
+        std::vector<int64_t> pool;
+        for (auto& m : members) {
+            const int64_t k = static_cast<int64_t>(m.size());
+            rng = seeded;
+            pool = m;
+            for (int64_t i = 0; i < k; ++i) {
+                const uint32_t j = rng.randbelow(static_cast<uint32_t>(k - i));
+                mix_out[m[static_cast<size_t>(i)]] = pool[j];
+                pool[j] = pool[static_cast<size_t>(k - i - 1)];
+            }
+        }
+    }
+    int32_t* mix32 = reinterpret_cast<int32_t*>(packed + off_mix);
+    for (int64_t b = 0; b < B; ++b) mix32[b] = static_cast<int32_t>(mix_out[b]);
+
+    // cycles running past the row end: blendable only if the clamped windows agree (pair_window's rule)
+    for (int64_t b = 0; b < B; ++b) {
+        const int32_t* f1 = f32 + b * 5;
+        const int32_t* f2 = f32 + mix_out[b] * 5;
+        if (f1[4] <= L && f2[4] <= L) continue;
+        for (int s = 0; s < 4; ++s) {
+            const int64_t n0 = std::min<int64_t>(f1[s + 1] - f1[s], f2[s + 1] - f2[s]);
+            const int64_t wd = std::min<int64_t>(f1[s] + n0, L) - std::min<int64_t>(f1[s], L);
+            const int64_t ws = std::min<int64_t>(f2[s] + n0, L) - std::min<int64_t>(f2[s], L);
+            if (wd != ws && !(wd == 0 && ws == 1)) {
+                info[5] = b; info[6] = s; info[7] = wd; info[8] = ws;
+                return 3;
+            }
+        }
+    }
+
+    if (want_order) {
+        int32_t* order = reinterpret_cast<int32_t*>(packed + off_order);
+        if (pcgmix_host_processing_order(mix_out, B, order) != 0) return 1;
+    }
+    return 0;
+}

@@ -22,6 +22,8 @@ ERR_BAD_FRAMES = 2
 ERR_BAD_PATTERN = 4
 ERR_OVERFLOW = 8
 ERR_ZERO_DIVISION = 16
+ERR_EMPTY_STATE = 32
+CYCLE_FEATURES = 36
 MAX_KNOT = 30
 
 _c_i32 = ctypes.c_int32
@@ -48,6 +50,7 @@ SIGNATURES = {
     "pcgmix_segment_table": [_ptr, _ptr, _ptr, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_cut_cycles": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _c_i32, _ptr],
     "pcgmix_duration_features": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
+    "pcgmix_cycle_features": [_ptr, _ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_mix1d_resident": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr, _c_f32, _c_f32,
                               _ptr, _ptr, _ptr, _c_i32, _ptr, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_copy_small": [_ptr, _ptr, ctypes.c_int64, _ptr],
@@ -55,6 +58,8 @@ SIGNATURES = {
     "pcgmix_host_lambda_knots": [ctypes.c_uint64, ctypes.c_double, ctypes.c_double, ctypes.c_int64, _c_i32,
                                  _ptr, _ptr, _ptr, _ptr, _ptr, _ptr],
     "pcgmix_host_processing_order": [_ptr, ctypes.c_int64, _ptr],
+    "pcgmix_host_prepare_step": [_ptr, ctypes.c_int64, _ptr, ctypes.c_int64, ctypes.c_int64, ctypes.c_uint64, _c_i32,
+                                 _c_i32, _c_i32, _ptr, ctypes.c_int64, _ptr, _ptr],
 }
 
 _lib = None
@@ -227,6 +232,44 @@ def host_lambda_knots(seed: int, alpha: float, sigma: float, shape, max_threads:
         raise ValueError("pcgmix_host_lambda_knots: the replay does not apply to these arguments")
     state = ("MT19937", key, pos.value, has_gauss.value, gauss.value) if want_state else None
     return lam.value, knots, state
+
+
+def host_prepare_step(labels, frames, length: int, seed: int, knot: int, channels: int, want_order: bool, packed):
+    """One foreign call for the integer half of a plain step (see ``pcgmix_host_prepare_step``): ``labels``
+    int64 (B,), ``frames`` int64 (B, >=5) CPU arrays, ``packed`` a pinned uint8 tensor.  Returns
+    ``(status, info, mix)`` — ``info`` the int64[16] layout / diagnostics block, ``mix`` the int64 pairing."""
+    import numpy as np
+    B = labels.shape[0]
+    info = np.zeros(16, dtype=np.int64)
+    mix = np.empty(B, dtype=np.int64)
+    rc = load().pcgmix_host_prepare_step(labels.ctypes.data, B, frames.ctypes.data, frames.strides[0] // 8, int(length),
+                                         int(seed), int(knot), int(channels), int(bool(want_order)), packed.data_ptr(),
+                                         packed.numel(), info.ctypes.data, mix.ctypes.data)
+    return rc, info, mix
+
+
+def mix1d_packed(x, out, tables, info, lam32, one_minus_lam32, coefmat=None, knot_pos=None, knot=-1, err_flag=None):
+    """``pcgmix_mix1d`` / ``pcgmix_mix1d_magwarp`` with the per-step tables taken from ONE device buffer at the
+    byte offsets ``info[0..3]`` written by ``host_prepare_step`` (no views, no re-validation: the layout was
+    produced by the library itself)."""
+    global launch_count
+    B, C, L = x.shape
+    base = tables.data_ptr()
+    order = base + int(info[2]) if info[2] >= 0 else None
+    dev = x.device
+    lib = load()
+    with _on_device(dev):
+        if knot < 0:
+            rc = lib.pcgmix_mix1d(x.data_ptr(), out.data_ptr(), base + int(info[0]), 5, base + int(info[1]), order,
+                                  float(lam32), float(one_minus_lam32), B, C, L,
+                                  _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+        else:
+            rc = lib.pcgmix_mix1d_magwarp(x.data_ptr(), out.data_ptr(), base + int(info[0]), 5, base + int(info[1]), order,
+                                          float(lam32), float(one_minus_lam32), base + int(info[3]), coefmat.data_ptr(),
+                                          knot_pos.data_ptr(), int(knot), B, C, L,
+                                          _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+    _check(rc, "pcgmix_mix1d (packed tables)")
+    launch_count += 1 if B > 0 else 0
 
 
 def host_processing_order(mix):
@@ -495,3 +538,23 @@ def duration_features(frames, n, fs, features, err_flag=None):
             _stream_handle(dev))
     _check(rc, "pcgmix_duration_features")
     launch_count += 1 if n > 0 else 0
+
+
+def cycle_features(x, frames, channel: int, what: int, features, err_flag=None):
+    """Amplitude (what & 1) and Hilbert-envelope (what & 2) features of ``x[:, channel]``; see
+    ``pcgmix_cycle_features`` in the header."""
+    global launch_count
+    if x.dim() != 3:
+        raise ValueError("x must be (B, C, L)")
+    B, C, L = x.shape
+    if tuple(features.shape) != (B, CYCLE_FEATURES):
+        raise ValueError(f"features must be (B, {CYCLE_FEATURES})")
+    _check_rows(B, frames=frames)
+    dev = _same_device(x, frames, features, err_flag)
+    fptr, fstride = _frames_ptr(frames)
+    with _on_device(dev):
+        rc = load().pcgmix_cycle_features(_dev_ptr(x, torch.float32, "x"), fptr, fstride, B, C, L, int(channel), int(what),
+                                          _dev_ptr(features, torch.float32, "features"),
+                                          _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+    _check(rc, "pcgmix_cycle_features")
+    launch_count += 1 if B > 0 else 0

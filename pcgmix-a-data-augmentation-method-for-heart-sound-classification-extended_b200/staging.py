@@ -42,6 +42,21 @@ class Uploader:
             slot.buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, pin_memory=True)
         return slot
 
+    def reserve(self, device: torch.device, nbytes: int) -> _Slot:
+        """A pinned staging slot of at least ``nbytes`` for the caller to fill (``slot.buf``); hand it to
+        :meth:`commit` afterwards."""
+        return self._slot(device, nbytes)
+
+    def commit(self, slot: _Slot, nbytes: int, device: torch.device) -> torch.Tensor:
+        """Upload the first ``nbytes`` of a filled slot; returns the device copy (uint8)."""
+        nbytes = (max(int(nbytes), _ALIGN) + _ALIGN - 1) // _ALIGN * _ALIGN
+        dev_buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        native.copy_small(dev_buf, slot.buf, nbytes)
+        if slot.event is None:
+            slot.event = torch.cuda.Event()
+        slot.event.record(torch.cuda.current_stream(device))
+        return dev_buf
+
     def upload(self, arrays: Sequence[np.ndarray], device: torch.device) -> List[torch.Tensor]:
         """Copy ``arrays`` (C-contiguous ndarrays) to ``device``; returns tensors of the same
         shapes/dtypes, all views into one device allocation."""
@@ -74,3 +89,11 @@ _default = Uploader()
 
 def upload(arrays: Sequence[np.ndarray], device) -> List[torch.Tensor]:
     return _default.upload(arrays, torch.device(device))
+
+
+def reserve(device, nbytes: int) -> _Slot:
+    return _default.reserve(torch.device(device), nbytes)
+
+
+def commit(slot: _Slot, nbytes: int, device) -> torch.Tensor:
+    return _default.commit(slot, nbytes, torch.device(device))

@@ -340,3 +340,40 @@ def test_host_labels_side_channel():
     assert tagged is ohe and np.array_equal(_common.labels_from_one_hot(ohe), [0, 1, 1, 0, 1])
     with pytest.raises(ValueError):
         _common.with_host_labels(ohe, torch.tensor([0, 1]))
+
+
+def test_prepare_step_packs_what_the_python_pieces_compute():
+    """`pcgmix_host_prepare_step` (the single-call host path of a plain step) against the separate Python/C++
+    pieces it replaces: pairing, int32 offsets, processing order, layout, and its refusals."""
+    rng = np.random.default_rng(11)
+    for batch, classes, want_order, knot, channels in ((64, 2, False, 4, 4), (257, 3, True, -1, 1), (1, 1, True, 2, 3), (4096, 2, True, 4, 4)):
+        frames = synth.cycle_frames(rng, batch, limit=2500).astype(np.int64)
+        wide = np.concatenate([frames, np.full((batch, 2), -7, np.int64)], axis=1)[:, :5]      # a strided (B, 5) view of (B, 7)
+        labels = rng.integers(0, classes, batch).astype(np.int64)
+        packed = torch.zeros(batch * 28 + max(0, batch * (knot + 2) * channels * 8) + 64, dtype=torch.uint8)
+        for step in (0, 5, 2 ** 32 - 1, 2 ** 40 + 3):
+            rc, info, mix = native.host_prepare_step(labels, wide, 2500, step, knot, channels, want_order, packed)
+            assert rc == 0
+            assert np.array_equal(mix, draws.same_label_pairing(labels, step))
+            raw = packed.numpy()
+            got_frames = raw[info[0]:info[0] + batch * 20].view(np.int32).reshape(batch, 5)
+            assert np.array_equal(got_frames, frames)
+            assert np.array_equal(raw[info[1]:info[1] + batch * 4].view(np.int32), mix)
+            if want_order:
+                assert np.array_equal(raw[info[2]:info[2] + batch * 4].view(np.int32), draws.processing_order(mix))
+            else:
+                assert info[2] == -1
+            assert (info[3] >= 0) == (knot >= 0) and all(o % 16 == 0 for o in info[:5] if o >= 0)
+            if knot >= 0:
+                assert info[4] >= info[3] + batch * (knot + 2) * channels * 8
+    # refusals
+    frames = np.array([[0, 10, 20, 30, 40], [0, 10, 5, 30, 40]], np.int64)
+    packed = torch.zeros(4096, dtype=torch.uint8)
+    rc, info, _ = native.host_prepare_step(np.zeros(2, np.int64), frames, 50, 1, -1, 1, False, packed)
+    assert rc == 2 and info[5] == 1
+    frames = np.array([[0, 10, 20, 30, 70], [0, 10, 20, 35, 75]], np.int64)            # both run past a row of 50, unequal clamps
+    rc, info, mix = native.host_prepare_step(np.zeros(2, np.int64), frames, 50, 0, -1, 1, False, packed)
+    if mix[0] == 1:
+        assert rc == 3 and info[6] == 3
+    rc, info, _ = native.host_prepare_step(np.zeros(2, np.int64), frames, 50, 0, 4, 4, True, torch.zeros(64, dtype=torch.uint8))
+    assert rc == 1 and info[4] > 64
