@@ -74,7 +74,10 @@ def parse_args():
                          "pipeline fill/drain through programmatic dependent launch)")
     ap.add_argument("--no-graph", action="store_true",
                     help="issue the K timed launches from Python instead of replaying them from one CUDA graph")
-    ap.add_argument("--debug-skip", type=int, default=0, help="profiling only: 1 no stores, 2 no arithmetic, 4 no partner staging")
+    ap.add_argument("--debug-skip", type=int, default=0,
+                    help="profiling build only (PCGMIX_PROFILING_LIB=1): 1 no stores, 2 no arithmetic, 4 no partner staging; "
+                         "outputs are wrong, so this implies --no-verify and is recorded in config")
+    ap.add_argument("--no-verify", action="store_true", help="do not check the timed outputs against the oracle")
     return ap.parse_args()
 
 
@@ -366,6 +369,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     native.load()
+    if os.environ.get("PCGMIX_SPLINE"):
+        native.set_spline_precision(os.environ["PCGMIX_SPLINE"])
     native.set_tuning(args.kernel == "pipeline", args.stages, args.max_slice, args.ctas_per_sm, args.pbuf_pct,
                       args.consumer_threads, args.debug_skip)
 

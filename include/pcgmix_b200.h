@@ -89,12 +89,26 @@ int pcgmix_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
  *   consumer_threads  lower bound on consumer threads per CTA (0 = just enough for one slice)
  *   debug         must be 0 in production.  Bits 0-4 switch parts of the pipelined kernel off for
  *                 profiling and give WRONG output (1 no stores, 2 no arithmetic, 4 no partner
- *                 staging, 8 no coefficient set-up, 16 no knot loads); bits 16-17 select the number
- *                 of 128-bit vectors per consumer thread (0 = default 2, 1 = one; same output)
+ *                 staging, 8 no coefficient set-up, 16 no knot loads, 64 no float32 safety check).  They
+ *                 exist only in a library built with -DPCGMIX_PROFILING; the default build refuses
+ *                 them.  Bit 5 (32: no coefficient table, every item takes the producers' per-item
+ *                 path) changes no result and is always honoured
  * Results do not depend on any of these.
  */
 int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, int32_t ctas_per_sm,
                       int32_t pbuf_pct, int32_t consumer_threads, int32_t debug);
+
+/*
+ * How the pipelined kernel evaluates the magnitude-warp factor of PCGmix+ (process-wide).
+ *   1 (default)  float32: normalised Horner on coefficients rounded from float64, fp32 product.  Within
+ *                1e-5 relative of the reference (BASELINE's tolerance; measured ~3e-7, factors below 1/16 in
+ *                magnitude are re-evaluated in float64), at the speed of plain PCGmix.
+ *   0            float64 Horner and one rounding of fp64(sample)*w to fp32, like the reference's float64
+ *                product stored into a float32 array: > 99.9 % of samples bit-equal to it, ~15 % slower.
+ * The direct-load kernels (short or unaligned rows) always evaluate in float64.
+ */
+int pcgmix_set_spline_precision(int32_t float32_evaluation);
+int pcgmix_get_spline_precision(void);
 
 /*
  * Launch overlap between consecutive PCGmix launches on one stream (default: off).

@@ -34,8 +34,27 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def _compile_one(src: str, obj: str, verbose: bool):
-    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "--shared"], "-I", INCLUDE, "-c", "-o", obj, src]
+PROFILING_LIB_PATH = os.path.join(CSRC, "libpcgmix_b200_prof.so")
+
+
+def build_profiling(verbose: bool = False) -> str:
+    """A second library with the pipelined kernel's skip switches compiled IN (-DPCGMIX_PROFILING): parts of the
+    kernel can be switched off through ``pcgmix_set_tuning(debug=...)`` to see what they cost — the output is then
+    WRONG.  Never loaded unless ``PCGMIX_PROFILING_LIB=1`` is set (benchmarks/skip_switch_sweep.py does)."""
+    from concurrent.futures import ThreadPoolExecutor
+    odir = os.path.join(OBJ_DIR, "prof")
+    os.makedirs(odir, exist_ok=True)
+    jobs = [(os.path.join(CSRC, n), os.path.join(odir, os.path.splitext(n)[0] + ".o")) for n in SOURCES]
+    with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+        list(pool.map(lambda j: _compile_one(j[0], j[1], verbose, ("-DPCGMIX_PROFILING",)), jobs))
+    proc = subprocess.run([_nvcc(), "--shared", "-o", PROFILING_LIB_PATH, *[j[1] for j in jobs]], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + proc.stdout + proc.stderr)
+    return PROFILING_LIB_PATH
+
+
+def _compile_one(src: str, obj: str, verbose: bool, extra=()):
+    cmd = [_nvcc(), *[f for f in NVCC_FLAGS if f != "--shared"], *extra, "-I", INCLUDE, "-c", "-o", obj, src]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     proc = subprocess.run(cmd, capture_output=True, text=True)

@@ -12,7 +12,7 @@ namespace {
 thread_local char g_error[512] = "";
 
 // Kernel-selection knobs (pcgmix_set_tuning).  Written and read under g_tuning_mutex: launches take a copy.
-pcgmix::PipelineTuning g_tuning = {1, 0, 0, 0, 0, 0, 0, 0};
+pcgmix::PipelineTuning g_tuning = {1, 0, 0, 0, 0, 0, 0, 0, 1};
 std::mutex g_tuning_mutex;
 
 pcgmix::PipelineTuning tuning_now() {
@@ -209,9 +209,26 @@ int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, i
     g_tuning.ctas_per_sm = ctas_per_sm;
     g_tuning.pbuf_pct = pbuf_pct;
     g_tuning.consumer_threads = consumer_threads;
+#ifdef PCGMIX_PROFILING
     g_tuning.debug = debug & 0xffff;
-    g_tuning.vec_per_thread = (debug >> 16) & 3;     // bits 16-17 of `debug` carry the vectors-per-thread knob
+#else
+    // bit 5 (no coefficient table: every item through the producers' per-item path) changes no result and stays
+    if (debug & 0xffdf) return fail("the skip switches exist only in a library built with -DPCGMIX_PROFILING");
+    g_tuning.debug = debug & 32;
+#endif
+    g_tuning.vec_per_thread = 0;
     return 0;
+}
+
+int pcgmix_set_spline_precision(int32_t float32_evaluation) {
+    std::lock_guard<std::mutex> lock(g_tuning_mutex);
+    g_tuning.spline_f32 = float32_evaluation ? 1 : 0;
+    return 0;
+}
+
+int pcgmix_get_spline_precision(void) {
+    std::lock_guard<std::mutex> lock(g_tuning_mutex);
+    return g_tuning.spline_f32;
 }
 
 long long pcgmix_overlap_launches(void) { return g_overlap_launches; }

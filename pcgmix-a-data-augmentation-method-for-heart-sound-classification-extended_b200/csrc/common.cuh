@@ -106,8 +106,9 @@ struct PipelineTuning {
     int ctas_per_sm;    // cap on resident CTAs per SM, 0 = as many as fit
     int pbuf_pct;       // shared-memory budget of the packed partner windows, % of a slice, 0 = default
     int consumer_threads;  // lower bound on consumer threads per CTA, 0 = just enough for a slice
-    int vec_per_thread; // 128-bit vectors per consumer thread and slice: 1 or 2 (0 = default 2)
+    int vec_per_thread; // (retired knob: the kernel always takes two 128-bit vectors per consumer thread and slice)
     int debug;          // profiling only (results become wrong): 1 skip stores, 2 skip arithmetic, 4 skip partner copies
+    int spline_f32;     // PCGmix+: 1 = warp factor in float32 (<= 1e-5 relative, default), 0 = float64 (bit-faithful)
 };
 bool pipeline_applicable(const MixArgs& a, bool box);
 // overlap_previous: launch with the programmatic-stream-serialization attribute, i.e. this kernel may start

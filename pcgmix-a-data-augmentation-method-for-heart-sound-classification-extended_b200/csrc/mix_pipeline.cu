@@ -50,6 +50,14 @@ namespace pcgmix {
 
 namespace {
 
+// Skip switches (pcgmix_set_tuning's `debug` bits) exist only in a library built with -DPCGMIX_PROFILING: they
+// make the kernel produce WRONG output fast and have no business in the shipped build.
+#ifdef PCGMIX_PROFILING
+#define PCGMIX_SKIP(bit) (pa.debug & (bit))
+#else
+#define PCGMIX_SKIP(bit) false
+#endif
+
 constexpr int kMaxStages = 8;
 constexpr int kHeaderBytes = 1024;
 constexpr int kProducerWarps = 2;       // producer warps take alternate items (one warp's instruction stream per
@@ -57,6 +65,12 @@ constexpr int kProducerWarps = 2;       // producer warps take alternate items (
 constexpr int kHelperThreads = 32 + 32 * kProducerWarps;   // the LAST warps of the CTA: store warp, then producers
                                        // (the SM's issue arbiter favours high warp ids; a producer in warp 0
                                        // is starved by consumer warps polling their barriers)
+// PCGmix+ replaces the second producer warp by the coefficient warp (see the kernel): its producers no longer
+// touch the knots, and a 14th warp would cost every thread 8 registers at three CTAs per SM
+__host__ __device__ constexpr int producer_warps(int warp_variant) { return warp_variant != 0 ? 1 : kProducerWarps; }
+__host__ __device__ constexpr int helper_threads(int warp_variant) {
+    return 32 + 32 * producer_warps(warp_variant) + (warp_variant != 0 ? 32 : 0);
+}
 
 struct StageMeta {
     int4 win[4];               // {local start, blended length, shift into pbase, local next start}
@@ -71,7 +85,9 @@ struct StageMeta {
     int own_shift;             // staged: floats between obuf[0] and column 0; -1: slice not staged (use own_g / pbase)
     int par_n;                 // not staged: partner columns (slice-local, before the window shift) that hold samples
     int positive;              // 1: the row's warp factor is certainly > 0 and finite at every sample
-    alignas(16) double coef[kMaxPieces * 4];
+    int exact;                 // float32 variant: 1 = coef holds float64 coefficients in powers of dt (the row's factor
+                               // may come close to zero); 0 = float32 coefficients in powers of u = dt/h
+    alignas(16) double coef[kMaxPieces * 4];    // written by the coefficient warp
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
@@ -133,6 +149,31 @@ __device__ __forceinline__ double int_to_double(int i) {
     return __hiloint2double(0x43300000, i) - 4503599627370496.0;
 }
 
+// Float32 variant, rows flagged `exact` by the coefficient warp (a factor that may come closer to zero than 1/16,
+// where the float32 evaluation's absolute error of ~3e-7 is no longer negligible relative to it): the consumers
+// blend such a row as usual, skip the float32 factor, and this pass then multiplies the thread's vectors in place
+// in float64, exactly like variant 1.  At the reference's sigma = 0.2 it runs for about one row in 10^5; it is
+// kept out of line so that the hot loop carries none of it.
+__device__ __noinline__ void exact_warp_pass(const MixArgs& a, const double* s_kpos, const int* s_kint, const double* coef,
+                                             float* xbuf, int nvec, int t_beg, int ct, int nct, int vpt) {
+    for (int k = 0; k < vpt; ++k) {
+        const int v = ct + k * nct;
+        if (v >= nvec) break;
+        float4 val = *reinterpret_cast<float4*>(xbuf + v * 4);
+        float r[4] = {val.x, val.y, val.z, val.w};
+        for (int e = 0; e < 4; ++e) {
+            const int t = t_beg + v * 4 + e;
+            int pe = min(static_cast<int>(__umulhi(static_cast<unsigned>(t), a.piece_magic)), a.K);
+            while (t >= s_kint[pe + 1]) ++pe;
+            const double de = __hiloint2double(0x43300000, t) - 4503599627370496.0 - s_kpos[pe];
+            const double* c = coef + pe * 4;
+            const double wv = fma(fma(fma(c[0], de, c[1]), de, c[2]), de, c[3]);
+            r[e] = static_cast<float>(static_cast<double>(r[e]) * wv);
+        }
+        *reinterpret_cast<float4*>(xbuf + v * 4) = make_float4(r[0], r[1], r[2], r[3]);
+    }
+}
+
 struct PipeArgs {
     int n_items;               // B * R * slices_per_row (checked < 2^31 by the launcher)
     int step_rest;             // gridDim.x / B  } item -> (slot, rest) advances by these per item,
@@ -146,14 +187,25 @@ struct PipeArgs {
     int stages;
     int stage_bytes;
     int header_bytes;          // barriers, knot tables and (PCGmix+) the coefficient matrix and table
-    int coef_items;            // PCGmix+: the spline coefficients of every CTA's first coef_items items are worked
-                               // out by the whole CTA before the pipeline starts (table behind the matrix)
     int debug;                 // profiling only: 1 = skip stores, 2 = skip arithmetic, 4 = skip partner copies
 };
 
-template <int NCT, bool MAGWARP, int VPT, bool RESIDENT>
-__global__ void __launch_bounds__(NCT + kHelperThreads, RESIDENT ? 2 : (NCT <= 192 ? 4 : NCT <= 320 ? 3 : 2))
+// WARP: 0 = PCGmix (no magnitude warp); 1 = PCGmix+ with the warp factor evaluated in float64 and the product
+// fp64(sample) * w rounded once to fp32, like the reference's float64 product stored into a float32 array
+// (> 99.9 % of samples bit-equal to it); 2 = PCGmix+ with the factor evaluated in float32 (normalised Horner,
+// coefficients rounded from float64) and an fp32 product: within 1e-5 relative of the reference (typically
+// 3e-7), at the cost of plain PCGmix — no float64 pipe, no conversions (see "PCGmix+ arithmetic" in DESIGN.md
+// for the ncu numbers that motivated it).  The absolute error of the float32 factor is ~3e-7, so the relative
+// bound needs |w| >= 1/16: the producer checks every row's knots against the bound that guarantees it
+// (|w - 1| <= Lambda * max_j |y_j - 1|, Lambda = Lebesgue constant of the knot -> curve map, from knot_pos[K+2]);
+// rows outside it (9 % at sigma = 0.2) and the K+1 vectors per row that contain a knot take variant 1's
+// float64 path, which is compiled into this variant too.
+template <int NCT, int WARP, int VPT, bool RESIDENT>
+__global__ void __launch_bounds__(NCT + helper_threads(WARP), RESIDENT ? 2 : (NCT <= 192 ? 4 : NCT <= 320 ? 3 : 2))
 mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ PipeArgs pa) {
+    constexpr bool MAGWARP = WARP != 0;
+    constexpr bool F32 = WARP == 2;
+    constexpr int kThreads = NCT + helper_threads(WARP);
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);                  // loads of the stage have landed
     uint64_t* computed = full + kMaxStages;                               // consumers are done with the stage
@@ -168,7 +220,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     // previous step's 330 MB of traffic.  The whole grid pulls them back with one L2 prefetch per
     // 128-byte line, so the producers' dependent chain order -> partner -> offsets runs on L2 hits.
     {
-        const long long gtid = static_cast<long long>(blockIdx.x) * (NCT + kHelperThreads) + threadIdx.x;
+        const long long gtid = static_cast<long long>(blockIdx.x) * kThreads + threadIdx.x;
         auto warm = [&](const void* base, long long bytes, long long first_line) {
             const long long line = gtid - first_line;
             if (base != nullptr && line >= 0 && line * 128 < bytes)
@@ -184,7 +236,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], MAGWARP ? 2 : 1);      // producer (+ the row's coefficients from the coefficient warp)
             mbar_init(&computed[s], NCT);
             mbar_init(&empty[s], 1);
         }
@@ -192,7 +244,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     }
     if constexpr (MAGWARP) {
         const int n_knots = a.K + 2;
-        for (int i = threadIdx.x; i < n_knots; i += NCT + kHelperThreads) {
+        for (int i = threadIdx.x; i < n_knots; i += kThreads) {
             const double kp = __ldg(a.knot_pos + i);
             s_kpos[i] = kp;
             s_kint[i] = (i == n_knots - 1) ? 0x7fffffff : static_cast<int>(ceil(kp));
@@ -200,7 +252,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         // The matrix must sit in shared memory: with ~216 KB of the SM carved out for the stage
         // rings, L1 is a few KB and a per-item walk over the matrix in global memory costs a chain
         // of L2 round trips in the producer (measured: 1.3 us per item, the whole kernel's bound).
-        for (int i = threadIdx.x; i < (a.K + 1) * 4 * n_knots; i += NCT + kHelperThreads) s_mat[i] = __ldg(a.coefmat + i);
+        for (int i = threadIdx.x; i < (a.K + 1) * 4 * n_knots; i += kThreads) s_mat[i] = __ldg(a.coefmat + i);
     }
     __syncthreads();
 
@@ -218,26 +270,135 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     // disjoint.  Harmless when nothing depends on us.
     if (threadIdx.x == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    const int n_coef_all = (a.K + 1) * 4;
-    double* s_tab = s_mat + n_coef_all * (a.K + 2);            // coefficient table, see the consumer branch
+    // piece width h = (P-1)/(K+1) in samples; coefficient i of a piece (of dt^(3-i)) times h^(3-i) is the
+    // coefficient of u^(3-i), u = dt/h in [0, 1)
+    const double h_piece = 1.0 / a.inv_h;
 
-    if (threadIdx.x >= NCT + 32) {
+    // item = rest * B + slot; this CTA's items are blockIdx.x, blockIdx.x + gridDim.x, ... (no division on the device)
+    struct Cursor { int slot, rest; };
+    auto advance1 = [&](Cursor c) {
+        c.slot += pa.step_slot;
+        c.rest += pa.step_rest;
+        if (c.slot >= a.B) {
+            c.slot -= a.B;
+            ++c.rest;
+        }
+        return c;
+    };
+    auto row_of = [&](Cursor c) { return pa.slices_per_row == 1 ? c.rest : c.rest / pa.slices_per_row; };
+
+    if (MAGWARP && threadIdx.x >= NCT + 32 + 32 * producer_warps(WARP)) {
+        // =================================== coefficient warp ====================================
+        // Turns every item's K+2 knots into the 4(K+1) cubic coefficients its consumers need (coefficient i =
+        // sum_j M[i][j] * knot_j, matrix in shared memory, knots broadcast by shuffle) and writes them into the
+        // item's stage, then arrives on the stage's `full` barrier next to the producer.  Nothing else depends
+        // on this arithmetic, so it runs beside the copies instead of in front of them: in the producers it sat
+        // in the dependent chain ahead of every load (6 us of 62 per launch), as a table built up front by the
+        // consumers it delayed the first items of every launch (3 us) — see profiles/README.md.
+        const int lane = threadIdx.x & 31;
+        const int n_knots = a.K + 2;
+        const int n_coef = (a.K + 1) * 4;
+        const bool wide = n_coef > 32;
+        auto knot_of = [&](Cursor c) {                      // lane j: knot j of the item's (cycle, row)
+            const int b = cycle_of_slot(a, c.slot);
+            double y = 0.0;
+            if (lane < n_knots && !PCGMIX_SKIP(16)) y = __ldg(a.knots + (static_cast<size_t>(b) * n_knots + lane) * a.R + row_of(c));
+            return y;
+        };
+        // knot_pos[K+2] = 0.999 / Lambda (Lambda: Lebesgue constant of the knot -> curve map): knots within that of 1
+        // keep the factor positive.  Rounded DOWN to fp32 and compared as bit patterns (non-negative floats order
+        // like unsigned integers; NaN orders above every bound).
+        unsigned safe_dev_bits = 0u;
+        if constexpr (RESIDENT) safe_dev_bits = __float_as_uint(__double2float_rd(fmax(__ldg(a.knot_pos + a.K + 2), 0.0)));
+        Cursor c0{static_cast<int>(blockIdx.x % a.B), static_cast<int>(blockIdx.x / a.B)};
+        Cursor c1 = advance1(c0);
+        double y_next = n_it > 0 ? knot_of(c0) : 0.0;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int it = 0; it < n_it; ++it) {
+            const double y_cur = y_next;
+            if (it + 1 < n_it) y_next = knot_of(c1);        // one item ahead: its latency hides behind this item's arithmetic
+            c1 = advance1(c1);
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;      // lane l owns coefficients l, l+32, l+64, l+96 (the last three: knot > 7)
+            const double* mrow = s_mat + lane * n_knots;
+            for (int j = 0; j < (PCGMIX_SKIP(8) ? 0 : n_knots); ++j) {
+                const double yj = __shfl_sync(kFullMask, y_cur, j);
+                if (lane < n_coef) acc0 = fma(mrow[j], yj, acc0);
+                if (wide) {
+                    if (lane + 32 < n_coef) acc1 = fma(mrow[32 * n_knots + j], yj, acc1);
+                    if (lane + 64 < n_coef) acc2 = fma(mrow[64 * n_knots + j], yj, acc2);
+                    if (lane + 96 < n_coef) acc3 = fma(mrow[96 * n_knots + j], yj, acc3);
+                }
+            }
+            // float32 variant: coefficients of u = dt/h (lane i: power 3 - (i & 3) of h), and is the factor certainly
+            // >= 1/16 on every piece?  A cubic on [0, 1] lies inside the hull of its Bernstein coefficients
+            // {d, d + c/3, d + 2c/3 + b/3, a + b + c + d}; lane i evaluates number (i & 3) of its piece.
+            int exact = 0;
+            float c32[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if constexpr (F32) {
+                const int power = 3 - (lane & 3);
+                const double scale = power == 3 ? h_piece * h_piece * h_piece : power == 2 ? h_piece * h_piece : power == 1 ? h_piece : 1.0;
+                c32[0] = static_cast<float>(acc0 * scale);
+                c32[1] = static_cast<float>(acc1 * scale);
+                c32[2] = static_cast<float>(acc2 * scale);
+                c32[3] = static_cast<float>(acc3 * scale);
+                float lowest = INFINITY;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    if (g > 0 && !wide) break;
+                    const int base = lane & ~3;
+                    const float ca = __shfl_sync(kFullMask, c32[g], base), cb = __shfl_sync(kFullMask, c32[g], base + 1);
+                    const float cc = __shfl_sync(kFullMask, c32[g], base + 2), cd = __shfl_sync(kFullMask, c32[g], base + 3);
+                    const int k = lane & 3;
+                    const float bern = k == 0 ? cd : k == 1 ? cd + cc * (1.0f / 3.0f)
+                                     : k == 2 ? cd + cc * (2.0f / 3.0f) + cb * (1.0f / 3.0f) : ca + cb + cc + cd;
+                    if (lane + 32 * g < n_coef) lowest = fminf(lowest, bern == bern ? bern : -INFINITY);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) lowest = fminf(lowest, __shfl_xor_sync(kFullMask, lowest, o));
+                exact = lowest >= 0.0625f ? 0 : 1;
+                if (PCGMIX_SKIP(64)) exact = 0;                 // (profiling: never take the float64 path)
+            }
+            // RESIDENT: the curve reproduces constants and is linear in the knots, |w(t) - 1| <= Lambda * max_j |y_j - 1|.
+            // Rows inside the bound have a positive, finite factor everywhere; consumers then write padding
+            // (exact +0.0f) without evaluating the spline.
+            int row_positive = 0;
+            if constexpr (RESIDENT) {
+                const float dev = lane < n_knots ? fabsf(static_cast<float>(y_cur) - 1.0f) : 0.0f;
+                row_positive = __reduce_max_sync(kFullMask, __float_as_uint(dev)) < safe_dev_bits ? 1 : 0;
+            }
+            mbar_wait(&empty[stage], phase ^ 1);            // the stage's previous slice has left shared memory
+            StageMeta* meta = stage_meta(stage);
+            if (F32 && !exact) {
+                float* out32 = reinterpret_cast<float*>(meta->coef);
+                if (lane < n_coef) out32[lane] = c32[0];
+                if (lane + 32 < n_coef) out32[lane + 32] = c32[1];
+                if (lane + 64 < n_coef) out32[lane + 64] = c32[2];
+                if (lane + 96 < n_coef) out32[lane + 96] = c32[3];
+            } else {
+                if (lane < n_coef) meta->coef[lane] = acc0;
+                if (lane + 32 < n_coef) meta->coef[lane + 32] = acc1;
+                if (lane + 64 < n_coef) meta->coef[lane + 64] = acc2;
+                if (lane + 96 < n_coef) meta->coef[lane + 96] = acc3;
+            }
+            if (lane == 0) {
+                meta->exact = exact;
+                meta->positive = row_positive;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[stage]);
+            if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    } else if (threadIdx.x >= NCT + 32) {
         // ===================================== producer warp =====================================
         const int lane = threadIdx.x & 31;
         const int pw = (threadIdx.x - (NCT + 32)) >> 5;      // this warp handles items pw, pw + kProducerWarps, ...
-        // order[slot] -> mix[b] -> frames[partner] (+ the row's knots) is a chain of dependent loads.
-        // It is software-pipelined across items: cycle ids are fetched three items ahead, partner
-        // ids two, offsets and knots one, so none of their latency sits in front of the copies.
-        struct Cursor { int slot, rest; };                  // item = rest * B + slot
-        auto advance1 = [&](Cursor c) {
-            c.slot += pa.step_slot;
-            c.rest += pa.step_rest;
-            if (c.slot >= a.B) {
-                c.slot -= a.B;
-                ++c.rest;
-            }
-            return c;
-        };
+        // order[slot] -> mix[b] -> frames[partner] is a chain of dependent loads.  It is software-pipelined
+        // across items: cycle ids are fetched three items ahead, partner ids two, offsets one, so none of
+        // their latency sits in front of the copies.
         auto advance = [&](Cursor c) {                      // to this warp's next item
             c.slot += pa.stepn_slot;
             c.rest += pa.stepn_rest;
@@ -248,14 +409,6 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             return c;
         };
         auto cycle_of = [&](Cursor c) { return cycle_of_slot(a, c.slot); };
-        auto row_of = [&](Cursor c) { return pa.slices_per_row == 1 ? c.rest : c.rest / pa.slices_per_row; };
-        auto knot_of = [&](int b, int row) {                // lane j holds knot j of (cycle b, row)
-            double y = 0.0;
-            if constexpr (MAGWARP) {
-                if (lane < a.K + 2 && !(pa.debug & 16)) y = __ldg(a.knots + (static_cast<size_t>(b) * (a.K + 2) + lane) * a.R + row);
-            }
-            return y;
-        };
         // per lane s: start of state s in the cycle (f1) and in the partner (f2); with explicit
         // windows ('(rand)' displacement) f1 = window start, f2 = f1 + shift, wn = blended length
         auto load_offsets = [&](int b, int p, int& f1, int& f2, int& wn) {
@@ -273,14 +426,8 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
         };
         int b0 = 0, b1 = 0, b2 = 0, p0 = 0, p1 = 0, f1 = 0, f2 = 0, wn = 0;
-        double y0 = 0.0;
         bool bad0 = false;
-        constexpr int NP = kProducerWarps;
-        // RESIDENT: knot_pos[K+2] is the largest knot deviation from 1 that keeps the warp factor positive
-        // (spline.safe_deviation; 0 disables the shortcut).  Rounded DOWN to fp32 and compared as bit patterns
-        // (non-negative floats order like unsigned integers; NaN orders above every bound).
-        unsigned safe_dev_bits = 0u;
-        if constexpr (RESIDENT && MAGWARP) safe_dev_bits = __float_as_uint(__double2float_rd(fmax(__ldg(a.knot_pos + a.K + 2), 0.0)));
+        constexpr int NP = producer_warps(WARP);
         // RESIDENT: the slot records are written by the kernel launched just before this one; everything
         // above (barriers, knot tables, coefficient matrix) did not need them
         if constexpr (RESIDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -293,7 +440,6 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             bad0 = static_cast<unsigned>(p0) >= static_cast<unsigned>(a.B);
             if (bad0) p0 = b0;
             load_offsets(b0, p0, f1, f2, wn);
-            if (RESIDENT || pw >= pa.coef_items) y0 = knot_of(b0, row_of(c0));
         }
         if (n_it > pw + NP) {
             b1 = cycle_of(c1);
@@ -310,14 +456,12 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             const int p = p0;
             const bool bad_partner = bad0;
             const int f1_cur = f1, f2_cur = f2, wn_cur = wn;
-            const double y_cur = y0;
             // prefetch for the items behind this one
             bool bad1 = false;
             if (it + NP < n_it) {
                 bad1 = static_cast<unsigned>(p1) >= static_cast<unsigned>(a.B);
                 if (bad1) p1 = b1;
                 load_offsets(b1, p1, f1, f2, wn);
-                if (RESIDENT || it + NP >= pa.coef_items) y0 = knot_of(b1, row_of(c1));
             }
             int p2 = 0, b3 = 0;
             if (it + 2 * NP < n_it) {
@@ -329,33 +473,6 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             b2 = b3;
             c0 = c1; c1 = c2; c2 = c3; c3 = advance(c3);
 
-            // coefficient i = sum_j M[i][j] * knot_j; knot_j comes from lane j by shuffle.  Lane l owns
-            // coefficients l, l+32, l+64, l+96; all but the first exist only for knot > 7.
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-            const bool tabled = MAGWARP && !RESIDENT && it < pa.coef_items;      // coefficients already in the CTA's table
-            if constexpr (MAGWARP) {
-                const int n_knots = a.K + 2;
-                const int n_coef = (a.K + 1) * 4;
-                const bool wide = n_coef > 32;
-                const double* mrow = s_mat + lane * n_knots;
-                for (int j = 0; j < ((pa.debug & 8) || tabled ? 0 : n_knots); ++j) {
-                    const double yj = __shfl_sync(kFullMask, y_cur, j);
-                    if (lane < n_coef) acc0 = fma(mrow[j], yj, acc0);
-                    if (wide) {
-                        if (lane + 32 < n_coef) acc1 = fma(mrow[32 * n_knots + j], yj, acc1);
-                        if (lane + 64 < n_coef) acc2 = fma(mrow[64 * n_knots + j], yj, acc2);
-                        if (lane + 96 < n_coef) acc3 = fma(mrow[96 * n_knots + j], yj, acc3);
-                    }
-                }
-            }
-            // The curve reproduces constants and is linear in the knots: |w(t) - 1| <= Lambda * max_j |y_j - 1|.
-            // Rows inside the bound have a positive, finite factor everywhere; consumers then write padding
-            // (exact +0.0f) without evaluating the spline.
-            int row_positive = 0;
-            if constexpr (RESIDENT && MAGWARP) {
-                const float dev = lane < a.K + 2 ? fabsf(static_cast<float>(y_cur) - 1.0f) : 0.0f;   // (no table in this variant)
-                row_positive = __reduce_max_sync(kFullMask, __float_as_uint(dev)) < safe_dev_bits ? 1 : 0;
-            }
             const int f1n = __shfl_down_sync(kFullMask, f1_cur, 1);
             const int f2n = __shfl_down_sync(kFullMask, f2_cur, 1);
             // window of state `lane`: start column, blended samples, shift to the partner's column (pair_window
@@ -410,7 +527,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             if constexpr (RESIDENT) {
                 if (own_first + t_beg - own_shift + own_cnt > a.n_sig) stageable = false;
             }
-            const bool staged = total <= pa.pbuf_cap && !(pa.debug & 4) && stageable;   // else: consumers read from global memory
+            const bool staged = total <= pa.pbuf_cap && !PCGMIX_SKIP(4) && stageable;   // else: consumers read from global memory
             if (!staged) {
                 have = false;
                 total = 0;
@@ -433,7 +550,6 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             if (lane == 0) {
                 meta->pbase = staged ? pbuf : (src_base + prow + t_beg);
                 if constexpr (RESIDENT) {
-                    meta->positive = row_positive;
                     meta->own_g = a.signal + own_first + t_beg;
                     meta->own_n = own_local;
                     meta->own_shift = staged ? own_shift : -1;
@@ -444,13 +560,6 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 meta->t_beg = t_beg;
                 const unsigned bad = (bad_partner ? PCGMIX_ERR_BAD_PARTNER : 0u) | (bad_frames ? PCGMIX_ERR_BAD_FRAMES : 0u);
                 if (bad != 0u && rest == 0 && a.err != nullptr) atomicOr(a.err, static_cast<int>(bad));
-            }
-            if (MAGWARP && !tabled) {
-                const int n_coef = (a.K + 1) * 4;
-                if (lane < n_coef) meta->coef[lane] = acc0;
-                if (lane + 32 < n_coef) meta->coef[lane + 32] = acc1;
-                if (lane + 64 < n_coef) meta->coef[lane + 64] = acc2;
-                if (lane + 96 < n_coef) meta->coef[lane + 96] = acc3;
             }
             __syncwarp();
             if constexpr (RESIDENT) {
@@ -482,7 +591,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             for (int it = 0; it < n_it; ++it) {
                 mbar_wait(&computed[stage], phase);
                 const StageMeta* m = stage_meta(stage);
-                if (!(pa.debug & 1)) bulk_store(a.out + m->out_offset, stage_x(stage), static_cast<uint32_t>(m->nvec) * 16u);
+                if (!PCGMIX_SKIP(1)) bulk_store(a.out + m->out_offset, stage_x(stage), static_cast<uint32_t>(m->nvec) * 16u);
                 bulk_store_wait_read(0);                   // the engine has read the slice out of shared memory
                 mbar_arrive(&empty[stage]);
                 if (++stage == S) {
@@ -495,50 +604,21 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     } else {
         // ===================================== consumer warps ====================================
         const int ct = threadIdx.x;
-        // PCGmix+: the coefficients of this CTA's items (coefficient matrix times the row's knots) are independent
-        // of everything else, so the consumer warps build them up front, while the producers already fill the
-        // first stages (nothing can be consumed for the first microsecond anyway) — instead of one producer warp
-        // doing it item by item inside its dependent chain (measured: 6 us of 62 per launch).  Same fma order as
-        // the producer's per-item path, which remains for items beyond the table.
-        if constexpr (MAGWARP && !RESIDENT) {
-            const int n_knots = a.K + 2;
-            const int tab_items = min(n_it, pa.coef_items);
-            // (item indices fit 32 bits: the launcher checks n_items < 2^31; loops kept rolled: this runs once)
-            auto row_of_item = [&](int q, int& b) {
-                const unsigned item = blockIdx.x + static_cast<unsigned>(q) * gridDim.x;
-                const unsigned rest = item / static_cast<unsigned>(a.B);
-                const int slot = static_cast<int>(item - rest * static_cast<unsigned>(a.B));
-                b = cycle_of_slot(a, slot);
-                return static_cast<int>(pa.slices_per_row == 1 ? rest : rest / static_cast<unsigned>(pa.slices_per_row));
-            };
-#pragma unroll 1
-            for (int task = threadIdx.x; task < tab_items * n_coef_all; task += NCT) {
-                const int q = task / n_coef_all;
-                const int i = task - q * n_coef_all;
-                int b;
-                const int row = row_of_item(q, b);
-                const double* y = a.knots + static_cast<size_t>(b) * n_knots * a.R + row;
-                const double* m = s_mat + i * n_knots;
-                double acc = 0.0;
-#pragma unroll 1
-                for (int j = 0; j < n_knots; ++j) acc = fma(m[j], __ldg(y + static_cast<size_t>(j) * a.R), acc);
-                s_tab[task] = acc;
-            }
-            asm volatile("bar.sync 1, %0;" ::"r"(NCT) : "memory");      // consumers only; producers and the store warp are long gone
-        }
-
         // With one slice per row a thread sees the same columns in every item, so which spline piece
         // they fall into (and the offset from the piece's knot) is found once, not once per vector.
         const bool fixed_cols = pa.slices_per_row == 1;
         int fixed_piece[VPT];
-        double fixed_dt[VPT];
+        double fixed_dt[F32 ? 1 : VPT];
+        float fixed_u[F32 ? VPT : 1];
+        const float du = static_cast<float>(a.inv_h);                           // one sample in units of u
         if constexpr (MAGWARP) {
 #pragma unroll
             for (int k = 0; k < VPT; ++k) {
                 const int t = min((ct + k * NCT) * 4, a.P - 4);
                 int piece = min(static_cast<int>(__umulhi(static_cast<unsigned>(t), a.piece_magic)), a.K);
                 while (t >= s_kint[piece + 1]) ++piece;
-                fixed_dt[k] = int_to_double(t) - s_kpos[piece];
+                const double dt = int_to_double(t) - s_kpos[piece];
+                if constexpr (F32) fixed_u[k] = static_cast<float>(dt * a.inv_h); else fixed_dt[k] = dt;
                 fixed_piece[k] = (t + 3 < s_kint[piece + 1]) ? piece : -1;      // -1: vector straddles a knot
             }
         }
@@ -547,13 +627,21 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         for (int it = 0; it < n_it; ++it) {
             float* xbuf = stage_x(stage);
             const StageMeta* meta = stage_meta(stage);
-            mbar_wait(&full[stage], phase);
+            // Only the first consumer warp polls the stage's barrier; the others park on a hardware barrier, which
+            // costs no issue slots.  With every warp polling, barrier polling was 35 % of all executed instructions
+            // (ncu, round 1) in a kernel whose SMs issue on ~60 % of their cycles.
+            if (ct < 32 || PCGMIX_SKIP(128)) mbar_wait(&full[stage], phase);
+            if (!PCGMIX_SKIP(128)) asm volatile("bar.sync 1, %0;" ::"r"(NCT) : "memory");
 
             const int lo1 = meta->win[1].x, lo2 = meta->win[2].x, lo3 = meta->win[3].x;
             const int nvec = meta->nvec;
             const int t_beg = meta->t_beg;
             const float* pbase = meta->pbase;
-            const double* coef = (MAGWARP && !RESIDENT && it < pa.coef_items) ? s_tab + static_cast<size_t>(it) * n_coef_all : meta->coef;
+            // float32 variant: a row whose factor may come close to zero (practically never: see the coefficient
+            // warp) is blended here and multiplied afterwards, in float64, by exact_warp_pass
+            const bool exact = F32 && meta->exact != 0;
+            const double* coef = meta->coef;
+            const float* coef32 = reinterpret_cast<const float*>(meta->coef);
             const float* obuf = stage_o(stage);
             const float* own_g = RESIDENT ? meta->own_g : nullptr;
             const int own_n = RESIDENT ? meta->own_n : 0;
@@ -563,7 +651,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
 #pragma unroll
             for (int k = 0; k < VPT; ++k) {
                 const int v = ct + k * NCT;
-                if (v < nvec && !(pa.debug & 2)) {
+                if (v < nvec && !PCGMIX_SKIP(2)) {
                     const int col = v * 4;                                   // local column
                     float r[4];
                     if constexpr (RESIDENT) {
@@ -635,7 +723,40 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                         *reinterpret_cast<float4*>(xbuf + col) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                         continue;
                     }
-                    if constexpr (MAGWARP) {
+                    if constexpr (F32) {
+                        if (!exact) {
+                            const int t = t_beg + col;
+                            int piece;
+                            float u0;
+                            if (fixed_cols) {
+                                piece = fixed_piece[k];
+                                u0 = fixed_u[k];
+                            } else {
+                                piece = min(static_cast<int>(__umulhi(static_cast<unsigned>(t), a.piece_magic)), a.K);
+                                while (t >= s_kint[piece + 1]) ++piece;
+                                u0 = static_cast<float>((int_to_double(t) - s_kpos[piece]) * a.inv_h);
+                                if (!(t + 3 < s_kint[piece + 1])) piece = -1;
+                            }
+                            if (__builtin_expect(piece >= 0, 1)) {
+                                const float4 c = *reinterpret_cast<const float4*>(coef32 + piece * 4);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float u = fmaf(static_cast<float>(e), du, u0);
+                                    r[e] = __fmul_rn(r[e], fmaf(fmaf(fmaf(c.x, u, c.y), u, c.z), u, c.w));
+                                }
+                            } else {                        // the vector contains a knot: piece per sample
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int te = t + e;
+                                    int pe = min(static_cast<int>(__umulhi(static_cast<unsigned>(te), a.piece_magic)), a.K);
+                                    while (te >= s_kint[pe + 1]) ++pe;
+                                    const float u = static_cast<float>((int_to_double(te) - s_kpos[pe]) * a.inv_h);
+                                    const float4 c = *reinterpret_cast<const float4*>(coef32 + pe * 4);
+                                    r[e] = __fmul_rn(r[e], fmaf(fmaf(fmaf(c.x, u, c.y), u, c.z), u, c.w));
+                                }
+                            }
+                        }
+                    } else if constexpr (MAGWARP) {
                         const int t = t_beg + col;
                         int piece;
                         double dt;
@@ -672,6 +793,9 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                     }
                     *reinterpret_cast<float4*>(xbuf + col) = make_float4(r[0], r[1], r[2], r[3]);
                 }
+            }
+            if constexpr (F32) {
+                if (__builtin_expect(exact, 0)) exact_warp_pass(a, s_kpos, s_kint, coef, xbuf, nvec, t_beg, ct, NCT, VPT);
             }
             fence_async_proxy();                           // my shared-memory writes -> visible to the TMA engine
             mbar_arrive(&computed[stage]);
@@ -716,7 +840,7 @@ struct GridPlan {
     unsigned long long* signature_out;
 };
 
-template <int NCT, bool MAGWARP, int VPT, bool RESIDENT>
+template <int NCT, int MAGWARP, int VPT, bool RESIDENT>
 cudaError_t launch_instance(const MixArgs& a, PipeArgs pa, size_t smem, GridPlan plan, cudaStream_t stream) {
     auto kernel = mix_pipeline_kernel<NCT, MAGWARP, VPT, RESIDENT>;
     // Per device and kernel instance: opt in to the large dynamic shared-memory carve-out (the attribute is
@@ -735,7 +859,7 @@ cudaError_t launch_instance(const MixArgs& a, PipeArgs pa, size_t smem, GridPlan
         }
         if (c.smem != smem || c.ctas == 0) {
             int n = 0;
-            const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NCT + kHelperThreads, smem);
+            const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NCT + helper_threads(MAGWARP), smem);
             if (e != cudaSuccess) return e;
             if (n < 1) return cudaErrorInvalidConfiguration;
             c.smem = smem;
@@ -759,11 +883,11 @@ cudaError_t launch_instance(const MixArgs& a, PipeArgs pa, size_t smem, GridPlan
     if (grid > pa.n_items) grid = pa.n_items;
     pa.step_rest = static_cast<int>(grid / a.B);
     pa.step_slot = static_cast<int>(grid % a.B);
-    pa.stepn_rest = static_cast<int>((grid * kProducerWarps) / a.B);
-    pa.stepn_slot = static_cast<int>((grid * kProducerWarps) % a.B);
+    pa.stepn_rest = static_cast<int>((grid * producer_warps(MAGWARP)) / a.B);
+    pa.stepn_slot = static_cast<int>((grid * producer_warps(MAGWARP)) % a.B);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(NCT + kHelperThreads);
+    cfg.blockDim = dim3(NCT + helper_threads(MAGWARP));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -775,9 +899,10 @@ cudaError_t launch_instance(const MixArgs& a, PipeArgs pa, size_t smem, GridPlan
 }
 
 template <int NCT, int VPT, bool RESIDENT>
-cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, size_t smem, bool magwarp, const GridPlan& plan, cudaStream_t stream) {
-    return magwarp ? launch_instance<NCT, true, VPT, RESIDENT>(a, pa, smem, plan, stream)
-                   : launch_instance<NCT, false, VPT, RESIDENT>(a, pa, smem, plan, stream);
+cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, size_t smem, int warp, const GridPlan& plan, cudaStream_t stream) {
+    return warp == 2 ? launch_instance<NCT, 2, VPT, RESIDENT>(a, pa, smem, plan, stream)
+         : warp == 1 ? launch_instance<NCT, 1, VPT, RESIDENT>(a, pa, smem, plan, stream)
+                     : launch_instance<NCT, 0, VPT, RESIDENT>(a, pa, smem, plan, stream);
 }
 
 }  // namespace
@@ -804,6 +929,7 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     DeviceFacts facts{};
     if (const cudaError_t e = device_facts(&device, &facts)) return e;
     const int g_sm_count = facts.sm_count;
+    const int warp = magwarp ? (tune.spline_f32 ? 2 : 1) : 0;      // kernel variant, see mix_pipeline_kernel
     PipeArgs pa{};
     const int max_slice = tune.max_slice > 0 ? (tune.max_slice > 3584 ? 3584 : tune.max_slice) : 3584;   // 448 threads x 2 vectors
     pa.slices_per_row = (a.P + max_slice - 1) / max_slice;
@@ -825,27 +951,11 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     const long long n_items = static_cast<long long>(a.B) * a.R * pa.slices_per_row;
     if (n_items > 2147483647LL) return cudaErrorInvalidConfiguration;
     pa.n_items = static_cast<int>(n_items);
-    // Coefficient table: as many of a CTA's items as fit into the shared memory the stage rings leave free
-    // without costing a resident CTA (the rest is done item by item by the producers).
-    const size_t bare_smem = ((kHeaderBytes + mat_bytes + 127) & ~static_cast<size_t>(127)) + static_cast<size_t>(pa.stages) * pa.stage_bytes;
-    if (bare_smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    pa.coef_items = 0;
-    if (magwarp && !resident && !(tune.debug & 32)) {   // (RESIDENT is consumer-bound: measured no gain there)
-        const int ctas = static_cast<int>((228 * 1024) / (bare_smem + 1024)) < 1 ? 1 : static_cast<int>((228 * 1024) / (bare_smem + 1024));
-        const size_t budget = (228 * 1024) / ctas - 1024 - 128;                 // what one CTA may use at this occupancy
-        const size_t per_item = static_cast<size_t>(a.K + 1) * 4 * sizeof(double);
-        const long long grid_guess = static_cast<long long>(g_sm_count) * ctas;
-        const long long per_cta = (n_items + grid_guess - 1) / grid_guess;
-        long long fit = budget > bare_smem ? static_cast<long long>((budget - bare_smem) / per_item) : 0;
-        if (fit > per_cta) fit = per_cta;
-        pa.coef_items = static_cast<int>(fit < 0 ? 0 : fit);
-    }
-    const size_t tab_bytes = static_cast<size_t>(pa.coef_items) * static_cast<size_t>(a.K + 1) * 4 * sizeof(double);
-    pa.header_bytes = static_cast<int>((kHeaderBytes + mat_bytes + tab_bytes + 127) & ~static_cast<size_t>(127));
+    pa.header_bytes = static_cast<int>((kHeaderBytes + mat_bytes + 127) & ~static_cast<size_t>(127));
     const size_t smem = pa.header_bytes + static_cast<size_t>(pa.stages) * pa.stage_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
-    pa.debug = tune.debug;
-    const int vpt = (tune.vec_per_thread == 1 && !resident) ? 1 : 2;
+    pa.debug = tune.debug;                                  // (the kernel reads it only in a PCGMIX_PROFILING build)
+    const int vpt = 2;                                                        // 128-bit vectors per consumer thread and slice
     const int need = ((slice_len / 4) + vpt - 1) / vpt;                       // consumer threads with work
     if (need > 448) return cudaErrorInvalidConfiguration;
     int nct = need <= 128 ? 128 : need <= 192 ? 192 : need <= 256 ? 256 : need <= 320 ? 320 : need <= 384 ? 384 : 448;
@@ -855,7 +965,7 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     }
     int per_sm = static_cast<int>((228 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : per_sm;
-    const int by_threads = 2048 / (nct + kHelperThreads);
+    const int by_threads = 2048 / (nct + helper_threads(warp));
     per_sm = per_sm < by_threads ? per_sm : by_threads;
     if (tune.ctas_per_sm > 0 && tune.ctas_per_sm < per_sm) per_sm = tune.ctas_per_sm;
     if (pa.stages < kProducerWarps) return cudaErrorInvalidConfiguration;
@@ -865,31 +975,21 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
         // kernel, which lets it start early; the producers wait for the records (griddepcontrol.wait)
         plan.overlap_previous = true;
         switch (nct) {
-            case 128: return launch_nct<128, 2, true>(a, pa, smem, magwarp, plan, stream);
-            case 192: return launch_nct<192, 2, true>(a, pa, smem, magwarp, plan, stream);
-            case 256: return launch_nct<256, 2, true>(a, pa, smem, magwarp, plan, stream);
-            case 320: return launch_nct<320, 2, true>(a, pa, smem, magwarp, plan, stream);
-            case 384: return launch_nct<384, 2, true>(a, pa, smem, magwarp, plan, stream);
-            default: return launch_nct<448, 2, true>(a, pa, smem, magwarp, plan, stream);
-        }
-    }
-    if (vpt == 1) {
-        switch (nct) {
-            case 128: return launch_nct<128, 1, false>(a, pa, smem, magwarp, plan, stream);
-            case 192: return launch_nct<192, 1, false>(a, pa, smem, magwarp, plan, stream);
-            case 256: return launch_nct<256, 1, false>(a, pa, smem, magwarp, plan, stream);
-            case 320: return launch_nct<320, 1, false>(a, pa, smem, magwarp, plan, stream);
-            case 384: return launch_nct<384, 1, false>(a, pa, smem, magwarp, plan, stream);
-            default: return launch_nct<448, 1, false>(a, pa, smem, magwarp, plan, stream);
+            case 128: return launch_nct<128, 2, true>(a, pa, smem, warp, plan, stream);
+            case 192: return launch_nct<192, 2, true>(a, pa, smem, warp, plan, stream);
+            case 256: return launch_nct<256, 2, true>(a, pa, smem, warp, plan, stream);
+            case 320: return launch_nct<320, 2, true>(a, pa, smem, warp, plan, stream);
+            case 384: return launch_nct<384, 2, true>(a, pa, smem, warp, plan, stream);
+            default: return launch_nct<448, 2, true>(a, pa, smem, warp, plan, stream);
         }
     }
     switch (nct) {
-        case 128: return launch_nct<128, 2, false>(a, pa, smem, magwarp, plan, stream);
-        case 192: return launch_nct<192, 2, false>(a, pa, smem, magwarp, plan, stream);
-        case 256: return launch_nct<256, 2, false>(a, pa, smem, magwarp, plan, stream);
-        case 320: return launch_nct<320, 2, false>(a, pa, smem, magwarp, plan, stream);
-        case 384: return launch_nct<384, 2, false>(a, pa, smem, magwarp, plan, stream);
-        default: return launch_nct<448, 2, false>(a, pa, smem, magwarp, plan, stream);
+        case 128: return launch_nct<128, 2, false>(a, pa, smem, warp, plan, stream);
+        case 192: return launch_nct<192, 2, false>(a, pa, smem, warp, plan, stream);
+        case 256: return launch_nct<256, 2, false>(a, pa, smem, warp, plan, stream);
+        case 320: return launch_nct<320, 2, false>(a, pa, smem, warp, plan, stream);
+        case 384: return launch_nct<384, 2, false>(a, pa, smem, warp, plan, stream);
+        default: return launch_nct<448, 2, false>(a, pa, smem, warp, plan, stream);
     }
 }
 

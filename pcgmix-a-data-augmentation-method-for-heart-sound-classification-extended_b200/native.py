@@ -38,6 +38,8 @@ SIGNATURES = {
     "pcgmix_device_info": [_ptr, _ptr, _ptr],
     "pcgmix_set_launch_overlap": [_c_i32],
     "pcgmix_overlap_launches": [],
+    "pcgmix_set_spline_precision": [_c_i32],
+    "pcgmix_get_spline_precision": [],
     "pcgmix_set_tuning": [_c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32],
     "pcgmix_mix1d": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _c_i32, _c_i32, _c_i32, _ptr, _ptr],
     "pcgmix_mix1d_magwarp": [_ptr, _ptr, _ptr, _c_i32, _ptr, _ptr, _c_f32, _c_f32, _ptr, _ptr, _ptr,
@@ -72,6 +74,9 @@ class NativeLibraryError(RuntimeError):
 
 
 def library_path() -> str:
+    # PCGMIX_PROFILING_LIB=1: the build with the skip switches compiled in (profiling scripts only)
+    if os.environ.get("PCGMIX_PROFILING_LIB") == "1" and os.path.exists(build_native.PROFILING_LIB_PATH):
+        return build_native.PROFILING_LIB_PATH
     return build_native.LIB_PATH
 
 
@@ -303,6 +308,18 @@ def set_launch_overlap(enable: bool):
     """Let consecutive, buffer-disjoint PCGmix launches on one stream overlap (programmatic dependent
     launch); see ``pcgmix_set_launch_overlap`` in the header for what the caller asserts."""
     _check(load().pcgmix_set_launch_overlap(int(bool(enable))), "pcgmix_set_launch_overlap")
+
+
+def set_spline_precision(precision: str):
+    """``"float32"`` (default: PCGmix+ warp factor evaluated in fp32, <= 1e-5 relative to the reference, as
+    fast as plain PCGmix) or ``"float64"`` (bit-faithful evaluation, ~15 % slower); pipelined kernel only."""
+    if precision not in ("float32", "float64"):
+        raise ValueError("precision must be 'float32' or 'float64'")
+    _check(load().pcgmix_set_spline_precision(1 if precision == "float32" else 0), "pcgmix_set_spline_precision")
+
+
+def spline_precision() -> str:
+    return "float32" if load().pcgmix_get_spline_precision() else "float64"
 
 
 def overlap_launches() -> int:

@@ -14,14 +14,24 @@ pytestmark = pytest.mark.gpu
 REL_TOL = 1e-5       # north_star: float outputs within 1e-5 relative of the NumPy reference
 
 
-@pytest.fixture(autouse=True, params=["pipeline", "direct"])
+@pytest.fixture(autouse=True, params=["pipeline", "pipeline-f32", "direct"])
 def kernel_choice(request):
-    """Every test runs twice: slot records + the persistent TMA-pipelined kernel (rows of >= 1024
-    samples, L % 4 == 0), and with the pipelined kernels switched off (direct-load kernel)."""
+    """Every parity test runs three times: through the persistent TMA-pipelined kernel (used for rows of
+    >= 1024 samples) with the PCGmix+ factor evaluated in float64 (bit-faithful to the reference's float64
+    spline) and in float32 (the library default: <= 1e-5 relative), and with the pipelined kernel switched off,
+    i.e. through the direct-load kernel only (always float64)."""
     from pcgmix_b200 import native
-    native.set_tuning(use_pipeline=request.param == "pipeline")
+    native.set_tuning(use_pipeline=request.param != "direct")
+    native.set_spline_precision("float32" if request.param.endswith("f32") else "float64")
     yield request.param
     native.set_tuning(use_pipeline=True)
+    native.set_spline_precision("float32")
+
+
+def _bit_faithful_warp():
+    """True when PCGmix+ outputs are expected to equal the float64 reference computation sample for sample."""
+    from pcgmix_b200 import native
+    return native.spline_precision() == "float64"
 
 
 class _Args:
@@ -102,7 +112,8 @@ def test_resident_against_cpu_oracle(method):
     else:
         denom = np.maximum(np.abs(want), np.finfo(np.float32).tiny)
         assert float(np.max(np.abs(got - want) / denom)) <= REL_TOL
-        assert np.mean(got == want) > 0.999
+        if _bit_faithful_warp():
+            assert np.mean(got == want) > 0.999
 
 
 def test_gate_fail_and_unknown_method_return_the_plain_batch():
