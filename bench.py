@@ -14,15 +14,23 @@ Numbers on the JSON line
                  draws (frames, pairing, order, knots) already uploaded: K kernel launches
                  between two CUDA events on the launching stream, max over ranks
   roofline ..... algorithmic bytes per launch 4*C*(2*L*B + sum_b M_b) over the mean launch time,
-                 against the measured HBM copy peak in MEASURED_PEAKS.json
+                 against the measured HBM copy peak in MEASURED_PEAKS.json; ``serialized_launches``
+                 is the same kernel with ordinary stream order and an event pair per launch;
+                 ``dram`` relates the ncu-measured DRAM traffic of a launch to the same times
+  verified ..... sampled cycles of the LAST timed outputs (device leg and e2e leg) recomputed by the
+                 CPU oracle; the run exits non-zero if they differ by more than 1e-5 relative
   e2e .......... the same metric through the public ``augmentations.augment`` call with HOST
                  buffers: pinned host batch -> device, host draws, kernel, result -> pinned host,
-                 all inside the timed region
-  cpu_baseline . the CPU oracle (a port of the reference's Python loop + SciPy splines) timed on
-                 this box's host cores on a bounded sample of the same workload
+                 all inside the timed region.  ``e2e_variants`` holds the same loop with fewer bytes
+                 on the PCIe link (what a training loop really moves): the result consumed on the
+                 device, and batches drawn from recordings that stay on the device
+  configs ...... device-timed legs of the other BASELINE configurations (cfg1, cfg3, cfg4, the resident
+                 path); cfg5 ..... the DDP training step fed by the on-device augmentation
+  cpu_baseline . the reference's own ``augment`` (byte-compiled under oracle/_ref) or, without it, the
+                 CPU oracle port, timed on this box's host cores on a bounded sample of the workload
 
-``--impl reference`` times only that CPU port (the reference itself is Python and is not
-available on the GPU box), spread over all host cores, and prints the same JSON shape.
+``--impl reference`` times only that CPU implementation, one process per host core, each running
+whole steps of the unmodified reference on its own batches, and prints the same JSON shape.
 """
 from __future__ import annotations
 
@@ -78,6 +86,14 @@ def parse_args():
                     help="profiling build only (PCGMIX_PROFILING_LIB=1): 1 no stores, 2 no arithmetic, 4 no partner staging; "
                          "outputs are wrong, so this implies --no-verify and is recorded in config")
     ap.add_argument("--no-verify", action="store_true", help="do not check the timed outputs against the oracle")
+    ap.add_argument("--no-configs", action="store_true", help="skip the device-timed legs of the other BASELINE configs")
+    ap.add_argument("--no-variants", action="store_true", help="skip the e2e variants (device-side consumer, resident recordings)")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the DDP training-step leg (BASELINE config 5)")
+    ap.add_argument("--cfg5-steps", type=int, default=40)
+    ap.add_argument("--spline", default=os.environ.get("PCGMIX_SPLINE", "float32"), choices=["float32", "float64"],
+                    help="how the pipelined kernel evaluates the warp factor (float32: library default, <= 1e-5 relative; "
+                         "float64: bit-faithful)")
+    ap.add_argument("--reference-sample", type=int, default=256, help="cycles per step of a reference-arm process")
     return ap.parse_args()
 
 
@@ -307,41 +323,137 @@ def measured_peak():
 # ----------------------------------------------------------------------------------------------
 # reference arm
 # ----------------------------------------------------------------------------------------------
+def _reference_worker(conn, method, sample, channels, length, seed, steps, warmup):
+    """One process of the reference arm: the UNMODIFIED reference ``augment`` (oracle/_ref, sourceless) on this
+    process's own batch, CPU tensors, one torch thread; reports the seconds its ``steps`` timed steps took."""
+    import torch
+    torch.set_num_threads(1)
+    from oracle.ref_import import load_reference
+    ref1, _ = load_reference(compiled=True)
+    data, frames, labels = make_batch(seed, sample, channels, length)
+    d = torch.from_numpy(data)
+    ohe = torch.nn.functional.one_hot(torch.from_numpy(labels), 2)
+    f = torch.from_numpy(frames)
+    wav = ["a0001"] * sample
+    a = _Args(method, sample)
+    for w in range(warmup):
+        ref1.augment(a, d, ohe, f, wav, _Step(w), None, "cpu", None)
+    conn.send("ready")
+    conn.recv()                                                # all processes start their timed steps together
+    t0 = time.perf_counter()
+    for k in range(steps):
+        ref1.augment(a, d, ohe, f, wav, _Step(warmup + k), None, "cpu", None)
+    conn.send(time.perf_counter() - t0)
+    conn.close()
+
+
+def time_reference(method, sample, channels, length, steps, warmup, workers):
+    """Cycles/s of the unmodified reference on this box: ``workers`` processes (one per host core), each running
+    whole steps of ``sample`` cycles on its own batch — the batches are independent, exactly as this repo's
+    ranks shard them.  Returns (cycles/s, seconds of the slowest process)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    procs, pipes = [], []
+    for w in range(workers):
+        parent, child = ctx.Pipe()
+        p = ctx.Process(target=_reference_worker, args=(child, method, sample, channels, length, 1000 + w, steps, warmup))
+        p.start()
+        procs.append(p)
+        pipes.append(parent)
+    for c in pipes:
+        c.recv()
+    for c in pipes:
+        c.send("go")
+    secs = [c.recv() for c in pipes]
+    for p in procs:
+        p.join()
+    return workers * steps * sample / max(secs), max(secs)
+
+
+def reference_kind():
+    from oracle.ref_import import compiled_reference_available
+    return "reference" if compiled_reference_available() else "port"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     workers = os.cpu_count() or 1
-    sample = min(args.batch, 1024)
-    data, frames, labels = make_batch(7, sample, args.channels, args.length)
-    from concurrent.futures import ProcessPoolExecutor
-    import multiprocessing as mp
-    pool = ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) if workers > 1 else None
-    try:
-        if pool is not None:
-            list(pool.map(_cpu_worker, [(data[:2], data[:2], frames[:2], frames[:2], 0.5, None)] * workers))
-        for w in range(args.warmup):
-            cpu_reference_step(args.method, data, frames, labels, w, pool, workers)
-        t0 = time.perf_counter()
-        for k in range(args.steps):
-            cpu_reference_step(args.method, data, frames, labels, args.warmup + k, pool, workers)
-        elapsed = time.perf_counter() - t0
-    finally:
-        if pool is not None:
-            pool.shutdown()
-    value = sample * args.steps / elapsed
-    sample_txt = (f"{args.steps} steps x {sample} cycles x {args.channels} ch x {args.length} samples of the same "
-                  f"workload (the full step is {args.batch} cycles; throughput of the per-cycle loop is flat in B)")
+    kind = reference_kind()
+    if kind == "reference":
+        sample = max(8, min(args.batch, args.reference_sample))
+        value, elapsed = time_reference(args.method, sample, args.channels, args.length, args.steps, args.warmup, workers)
+        sample_txt = (f"{workers} processes x {args.steps} steps x {sample} cycles x {args.channels} ch x {args.length} samples: the "
+                      f"unmodified reference augment() (oracle/_ref, byte-compiled from the reference tree), one process per host "
+                      f"core, each on its own batches (the full step is {args.batch} cycles; the reference's per-cycle loop is flat in B)")
+        ms_per_step = 1e3 * elapsed / args.steps
+    else:
+        sample = min(args.batch, 1024)
+        data, frames, labels = make_batch(7, sample, args.channels, args.length)
+        from concurrent.futures import ProcessPoolExecutor
+        import multiprocessing as mp
+        pool = ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) if workers > 1 else None
+        try:
+            if pool is not None:
+                list(pool.map(_cpu_worker, [(data[:2], data[:2], frames[:2], frames[:2], 0.5, None)] * workers))
+            for w in range(args.warmup):
+                cpu_reference_step(args.method, data, frames, labels, w, pool, workers)
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                cpu_reference_step(args.method, data, frames, labels, args.warmup + k, pool, workers)
+            elapsed = time.perf_counter() - t0
+        finally:
+            if pool is not None:
+                pool.shutdown()
+        value = sample * args.steps / elapsed
+        sample_txt = (f"{args.steps} steps x {sample} cycles x {args.channels} ch x {args.length} samples of the same workload through the "
+                      f"oracle PORT of the reference loop (oracle/_ref not built), per-cycle work spread over {workers} processes")
+        ms_per_step = 1e3 * elapsed / args.steps
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 mix, f64 spline",
         "data": "synthetic", "config": {"workload": WORKLOAD, "method": args.method, "sample": sample_txt},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample_txt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# verification of timed outputs against the CPU oracle
+# ----------------------------------------------------------------------------------------------
+def oracle_cycles(method, data, frames, mix, lam32, knots, sample):
+    """What the reference computes for cycles ``sample`` of a batch: per-pair blend (oracle.mix_pair) and, for
+    PCGmix+, the SciPy not-a-knot spline of the cycle's knots times the blend in float64, stored as float32."""
+    from oracle import pcgmix_oracle as orc
+    mixed = np.stack([orc.mix_pair(data[i], data[mix[i]], frames[i], frames[mix[i]], np.float32(lam32)) for i in sample])
+    if knots is None:
+        return mixed
+    curves = orc.warp_curves(data.shape[-1], knots[sample])
+    return (mixed.astype(np.float64) * curves).astype(np.float32)
+
+
+class Verifier:
+    """Accumulates comparisons of sampled output cycles with the oracle."""
+
+    def __init__(self, tolerance=1e-5):
+        self.tolerance, self.cycles, self.max_rel, self.equal, self.total = tolerance, 0, 0.0, 0, 0
+
+    def check(self, got, want):
+        denom = np.maximum(np.abs(want.astype(np.float64)), np.finfo(np.float32).tiny)
+        rel = np.abs(got.astype(np.float64) - want.astype(np.float64)) / denom
+        self.max_rel = max(self.max_rel, float(rel.max()))
+        self.equal += int((got.view(np.uint32) == want.view(np.uint32)).sum())
+        self.total += got.size
+        self.cycles += got.shape[0]
+
+    def report(self):
+        return {"cycles": self.cycles, "max_rel": self.max_rel, "bit_equal": self.equal / max(self.total, 1),
+                "tolerance": self.tolerance, "ok": self.cycles > 0 and self.max_rel <= self.tolerance,
+                "against": "oracle/pcgmix_oracle.py (per-pair blend + SciPy not-a-knot spline, float64 product)"}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -351,13 +463,13 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from pcgmix_b200 import augmentations, draws, native, spline, staging, synth
+    from pcgmix_b200 import augmentations, draws, native, resident, spline, staging, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU port")
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     local_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
@@ -369,10 +481,10 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     native.load()
-    if os.environ.get("PCGMIX_SPLINE"):
-        native.set_spline_precision(os.environ["PCGMIX_SPLINE"])
+    native.set_spline_precision(args.spline)
     native.set_tuning(args.kernel == "pipeline", args.stages, args.max_slice, args.ctas_per_sm, args.pbuf_pct,
                       args.consumer_threads, args.debug_skip)
+    verify = not args.no_verify and args.debug_skip == 0
 
     B, C, L = args.batch, args.channels, args.length
     K, W = args.steps, args.warmup
@@ -393,13 +505,20 @@ def run_b200(args):
         data, frames, labels = batches[s % NB]
         seed = rank * (W + K) + s                       # the "training step" of this batch
         mix = draws.same_label_pairing(labels, seed)
-        lam32, oml = draws.lambda_pair_fp32(draws.draw_lambda(plan.alpha, seed))
+        knots = None
+        if magwarp:
+            lam, knots = draws.lambda_and_knots(plan.alpha, seed, B, plan.knot, C, plan.sigma)
+        else:
+            lam = draws.draw_lambda(plan.alpha, seed)
+        lam32, oml = draws.lambda_pair_fp32(lam)
         arrays = [frames.astype(np.int32), mix.astype(np.int32),
                   np.arange(B, dtype=np.int32) if args.no_order else draws.processing_order(mix)]
         if magwarp:
-            arrays.append(draws.draw_knots(B, plan.knot, C, plan.sigma))
+            arrays.append(knots)
         on_dev = staging.upload(arrays, dev)
-        steps_meta.append({"dev": on_dev, "lam": (lam32, oml), "M": synth.mixed_samples(frames, mix)})
+        keep = s >= W + K - NOUT                                 # host copies of the last steps' draws, for the verification
+        steps_meta.append({"dev": on_dev, "lam": (lam32, oml), "M": synth.mixed_samples(frames, mix),
+                           "mix": mix if keep else None, "knots": knots if keep else None})
     torch.cuda.synchronize()
 
     # every step's launch is resolved once (pointers, sizes), so that issuing it is one foreign call
@@ -414,7 +533,7 @@ def run_b200(args):
     def launch(s):
         prepared[s].launch(stream_handle)
 
-    # consecutive steps are independent (distinct input batches, two alternating output buffers): let
+    # consecutive steps are independent (distinct input batches, three rotating output buffers): let
     # launch k+1 fill its pipeline while launch k drains; the library re-checks buffer disjointness
     native.set_launch_overlap(not args.no_launch_overlap)
     for s in range(W):
@@ -438,13 +557,16 @@ def run_b200(args):
     # them) and replayed: the host issues nothing inside the timed region, so ranks do not drift apart
     # with host scheduling noise.  --no-graph / --no-launch-overlap launch from Python instead.
     graph = None
+    overlapped_in_graph = 0
     if not per_launch_events and not args.no_graph:
         try:
             graph = torch.cuda.CUDAGraph()
+            before = native.overlap_launches()
             with torch.cuda.graph(graph):
                 capture_handle = torch.cuda.current_stream(dev).cuda_stream
                 for k in range(K):
                     prepared[W + k].launch(capture_handle)
+            overlapped_in_graph = native.overlap_launches() - before      # launches the library issued with the overlap attribute
             graph.replay()                                      # untimed: instantiate + upload
             torch.cuda.synchronize()
         except Exception as exc:                                # capture unsupported: fall back to direct launches
@@ -470,7 +592,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     t_end = time.perf_counter()
     gpu_launches = K if graph is not None else native.launch_count - launches_before
-    overlapped = (K - 1 if graph is not None else native.overlap_launches() - overlap_before)
+    overlapped = overlapped_in_graph if graph is not None else native.overlap_launches() - overlap_before
     native.set_launch_overlap(False)
     if world > 1:
         dist.barrier()
@@ -478,6 +600,18 @@ def run_b200(args):
     total_ms = marks[0].elapsed_time(marks[-1])
     per_launch_ms = ([marks[k].elapsed_time(marks[k + 1]) for k in range(K)] if per_launch_events else [total_ms / K])
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+
+    # ---- the timed region's own outputs against the oracle (the last NOUT steps still sit in the output buffers) ----
+    verifier = Verifier()
+    if verify:
+        vr = np.random.default_rng(12345 + rank)
+        for s in range(max(W, W + K - NOUT), W + K):
+            data, frames, labels = batches[s % NB]
+            sample = np.sort(vr.choice(B, min(32, B), replace=False))
+            got = outs[s % NOUT][torch.from_numpy(sample).to(dev)].cpu().numpy()
+            want = oracle_cycles(args.method, data, frames, steps_meta[s]["mix"], steps_meta[s]["lam"][0],
+                                 steps_meta[s]["knots"], sample)
+            verifier.check(got, want)
 
     # the same K steps once more with ordinary stream serialisation and an event pair around every
     # launch: per-launch statistics, reported next to the headline for comparison
@@ -523,6 +657,7 @@ def run_b200(args):
     in_ready = [torch.cuda.Event() for _ in range(NIN)]
     in_free = [torch.cuda.Event() for _ in range(NIN)]
     out_done = [torch.cuda.Event() for _ in range(2)]
+    checksum_host = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(2)]
 
     def stage_in(i):
         with torch.cuda.stream(s_in):
@@ -531,8 +666,12 @@ def run_b200(args):
             in_ready[i % NIN].record(s_in)
 
     host_s = [0.0]                                             # wall time spent inside augment() (draws + launch)
+    last = {}
 
-    def run_e2e(n, seed0):
+    def run_e2e(n, seed0, result="host"):
+        """``result``: "host" = the augmented batch goes back to pinned host memory (164 MB per step);
+        "device" = it is consumed on the device (what a training step does) and only a per-cycle checksum
+        (16 KB) is read back."""
         for ev in in_free + out_done:
             ev.record(stream)
         stage_in(0)
@@ -544,66 +683,176 @@ def run_b200(args):
                 stage_in(i + 2)
             stream.wait_event(in_ready[i % NIN])
             h0 = time.perf_counter()
-            out, _, _, _ = augmentations.augment(a, dev_in[i % NIN], ohe_t[j], frames_t[j], wav, _Step(seed0 + i), None, dev, None)
+            out, _, mix_i, _ = augmentations.augment(a, dev_in[i % NIN], ohe_t[j], frames_t[j], wav, _Step(seed0 + i), None, dev, None)
             host_s[0] += time.perf_counter() - h0
             in_free[i % NIN].record(stream)
+            if result == "device":
+                sums = out.sum(dim=(1, 2))                     # the device-side consumer's stand-in
             done = torch.cuda.Event()
             done.record(stream)
+            out_done[i % 2].synchronize()                      # the host has the result of step i-2 (and would consume it now)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(done)
-                s_out.wait_event(out_done[i % 2])              # host_out slot is free again
-                host_out[i % 2].copy_(out, non_blocking=True)
+                if result == "device":
+                    checksum_host[i % 2].copy_(sums, non_blocking=True)
+                    sums.record_stream(s_out)
+                else:
+                    host_out[i % 2].copy_(out, non_blocking=True)
                 out.record_stream(s_out)
                 out_done[i % 2].record(s_out)
+            last.update(step=seed0 + i, slot=i % 2, batch=j, mix=mix_i)
         stream.wait_stream(s_out)
         stream.wait_stream(s_in)
 
-    run_e2e(3, 10_000)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    def time_loop(fn, n, seed0, **kw):
+        fn(3, seed0 - 1000, **kw)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wall0 = time.perf_counter()
+        e0.record(stream)
+        fn(n, seed0, **kw)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - wall0) * 1e3
+        ms = max(e0.elapsed_time(e1), wall_ms)                 # host work is part of the step: take the longer clock
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
     launches_e2e0 = native.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    wall0 = time.perf_counter()
-    e0.record(stream)
     host_s[0] = 0.0
-    run_e2e(E, 20_000 + rank * E)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - wall0) * 1e3
-    e2e_ms = max(e0.elapsed_time(e1), wall_ms)          # host work is part of the step: take the longer clock
-    te = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * E * B / (float(te.item()) * 1e-3)
+    e2e_ms_total = time_loop(run_e2e, E, 20_000 + rank * E)
+    host_inside_ms = 1e3 * host_s[0] / (E + 3)
+    e2e_value = world * E * B / (e2e_ms_total * 1e-3)
     e2e_launches = native.launch_count - launches_e2e0
+    if verify:                                                 # the last e2e result, as it arrived in pinned host memory
+        data, frames, labels = batches[last["batch"]]
+        np.random.seed(last["step"])
+        lam_e = np.random.beta(plan.alpha, plan.alpha)
+        knots_e = np.random.normal(1.0, plan.sigma, (B, plan.knot + 2, C)) if magwarp else None
+        sample = np.sort(np.random.default_rng(777 + rank).choice(B, min(32, B), replace=False))
+        want = oracle_cycles(args.method, data, frames, last["mix"], draws.lambda_pair_fp32(lam_e)[0], knots_e, sample)
+        verifier.check(host_out[last["slot"]].numpy()[sample], want)
     # the host share of a step on its own (no GPU involved): the draws augment() makes for one batch
     t_h = time.perf_counter()
     for rep in range(5):
         m_ = draws.pairing(args.method, batches[0][2], wav, 30_000 + rep)
-        draws.lambda_pair_fp32(draws.draw_lambda(plan.alpha, 30_000 + rep))
         if magwarp:
-            draws.draw_knots(B, plan.knot, C, plan.sigma)
-        m_.astype(np.int32)
+            draws.lambda_and_knots(plan.alpha, 30_000 + rep, B, plan.knot, C, plan.sigma)
+        else:
+            draws.draw_lambda(plan.alpha, 30_000 + rep)
+        if augmentations.use_processing_order:
+            draws.processing_order(m_)
     host_draws_ms = (time.perf_counter() - t_h) / 5 * 1e3
     in_bytes = B * C * L * 4
     small_bytes = B * 5 * 4 + B * 4 * 2 + (B * (plan.knot + 2) * C * 8 if magwarp else 0)
+
+    # ---- the same loop with fewer bytes on the link ---------------------------------------------
+    variants = {}
+    if not args.no_variants:
+        ms_dev = time_loop(run_e2e, E, 40_000 + rank * E, result="device")
+        variants["padded_batch_up_result_consumed_on_device"] = {
+            "value": world * E * B / (ms_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_dev / E,
+            "h2d_bytes_per_step": in_bytes + small_bytes, "d2h_bytes_per_step": B * 4 + B * 8,
+            "what": "train_model.py:499-507 as it is: data.to(device) of the padded batch, augment(); the result stays on the "
+                    "device (its consumer is the model) and a per-cycle checksum is read back"}
+        # batches drawn from recordings that stay on the device: per step only table rows + draws go up
+        rr = np.random.default_rng(synth.BENCH_SEED + 77 + rank)
+        n_rec, t_rec = 256, 40000
+        st = torch.from_numpy(synth.dense_states(rr, n_rec, t_rec, 1000)).to(dev)
+        sig = torch.from_numpy(rr.standard_normal((n_rec, C, t_rec)).astype(np.float32)).to(dev)
+        res = resident.from_dense_states(sig, st, L)
+        ids_host = [rr.integers(0, res.n_cycles, B) for _ in range(4)]
+        tgt_host = [torch.from_numpy(rr.integers(0, 2, B)) for _ in range(4)]
+        ohe_r = [augmentations.with_host_labels(torch.nn.functional.one_hot(t_, 2).to(dev), t_) for t_ in tgt_host]
+
+        def run_resident(n, seed0, result="host"):
+            for ev in out_done:
+                ev.record(stream)
+            for i in range(n):
+                out, _, _, _ = resident.augment(a, res, ids_host[i % 4], ohe_r[i % 4], None, _Step(seed0 + i), None, dev, None)
+                if result == "device":
+                    sums = out.sum(dim=(1, 2))
+                done = torch.cuda.Event()
+                done.record(stream)
+                out_done[i % 2].synchronize()                  # the host has the result of step i-2
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(done)
+                    if result == "device":
+                        checksum_host[i % 2].copy_(sums, non_blocking=True)
+                        sums.record_stream(s_out)
+                    else:
+                        host_out[i % 2].copy_(out, non_blocking=True)
+                    out.record_stream(s_out)
+                    out_done[i % 2].record(s_out)
+            stream.wait_stream(s_out)
+
+        ms_res = time_loop(run_resident, E, 50_000 + rank * E)
+        ms_res_dev = time_loop(run_resident, E, 60_000 + rank * E, result="device")
+        res.check()
+        up_res = B * 4 + B * 4 + (B * (plan.knot + 2) * C * 8 if magwarp else 0)
+        variants["resident_recordings_result_to_host"] = {
+            "value": world * E * B / (ms_res * 1e-3), "unit": UNIT, "ms_per_step": ms_res / E,
+            "h2d_bytes_per_step": up_res, "d2h_bytes_per_step": in_bytes,
+            "what": "pcgmix_b200.resident.augment: recordings + cycle table stay on the device (uploaded once), per step the "
+                    "batch's table rows, pairing and knots go up and the augmented batch comes back to pinned host memory"}
+        variants["resident_recordings_result_consumed_on_device"] = {
+            "value": world * E * B / (ms_res_dev * 1e-3), "unit": UNIT, "ms_per_step": ms_res_dev / E,
+            "h2d_bytes_per_step": up_res, "d2h_bytes_per_step": B * 4,
+            "what": "the same with the result consumed on the device (per-cycle checksum read back): bounded by the host's "
+                    "draws, not by the link"}
+        del st, sig, res
+
+    # ---- device-timed legs of the other BASELINE configurations (rank 0's GPU; every rank runs them so that ranks stay in step)
+    configs = None
+    if not args.no_configs:
+        sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+        import run_configs
+        run_configs.PEAK = peak
+        lines = run_configs.collect(dev, reps=max(20, min(K, 60)))
+        configs = [{k: v for k, v in ln.items() if k in ("config", "cycles_per_call", "ms_mean", "ms_min", "cycles_per_s",
+                                                          "achieved_GBps", "frac_of_measured_peak", "host_draws_ms_total",
+                                                          "wall_ms_including_host_draws", "cycles_per_s_including_host_draws")}
+                   for ln in lines]
+    native.set_spline_precision(args.spline)
+
+    # ---- BASELINE config 5: the DDP training step fed by the on-device augmentation ----------------
+    cfg5 = None
+    if not args.no_cfg5:
+        sys.path.insert(0, os.path.join(ROOT, "examples"))
+        import train_ddp_pcgmix
+        cfg5 = {"padded_batches": train_ddp_pcgmix.run_cfg5(args.cfg5_steps, 64, False, False, init_process_group=False),
+                "resident_recordings": train_ddp_pcgmix.run_cfg5(args.cfg5_steps, 64, True, False, init_process_group=False)}
 
     # ---- CPU baseline on rank 0 at N=1 ----------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         workers = os.cpu_count() or 1
-        sample_b = 1024
-        v, done, elapsed, _ = time_cpu_baseline(args.method, sample_b, C, L, args.cpu_seconds, workers)
-        cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
-               "sample": f"{done} cycles ({done // sample_b} steps of {sample_b} x {C} ch x {L}) in {elapsed:.1f} s; "
-                         f"oracle port of the reference loop, per-cycle work spread over {workers} processes"}
+        if reference_kind() == "reference":
+            sample_b = max(8, min(B, args.reference_sample))
+            steps_ref = 2
+            t0 = time.perf_counter()
+            v, _ = time_reference(args.method, sample_b, C, L, steps_ref, 1, workers)
+            cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "reference",
+                   "sample": f"{workers} processes x {steps_ref} steps x {sample_b} cycles x {C} ch x {L}: the unmodified reference "
+                             f"augment() (oracle/_ref), one process per host core; {time.perf_counter() - t0:.1f} s in all"}
+        else:
+            sample_b = 1024
+            v, done, elapsed, _ = time_cpu_baseline(args.method, sample_b, C, L, args.cpu_seconds, workers)
+            cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "port",
+                   "sample": f"{done} cycles ({done // sample_b} steps of {sample_b} x {C} ch x {L}) in {elapsed:.1f} s; "
+                             f"oracle port of the reference loop, per-cycle work spread over {workers} processes"}
 
+    verified = verifier.report() if verify else {"ok": None, "skipped": "--no-verify or --debug-skip"}
     if rank == 0:
+        serial_mean = statistics.fmean(serial_ms)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 mix, f64 spline", "data": "synthetic",
+            "dtype": "f32 mix, " + ("f32" if args.spline == "float32" else "f64") + " spline", "data": "synthetic",
             "config": {"workload": WORKLOAD if (B, C, L, args.method) == (4096, 4, 2500, METHOD) else
                        f"{args.method} on {B} cycles x {C} ch x {L} samples per GPU",
                        "method": args.method, "cycles_per_step_per_gpu": B, "channels": C, "samples": L,
@@ -614,34 +863,56 @@ def run_b200(args):
                        "launch_overlap": "off" if args.no_launch_overlap else
                        "programmatic dependent launch between consecutive independent steps (buffers checked disjoint)",
                        "launch_mode": "one CUDA graph of K kernel nodes, replayed" if graph is not None else "K launches from Python",
-                       "kernel": args.kernel, "stages": args.stages, "max_slice": args.max_slice, "ctas_per_sm": args.ctas_per_sm,
+                       "kernel": args.kernel, "spline_evaluation": args.spline, "stages": args.stages, "max_slice": args.max_slice,
+                       "ctas_per_sm": args.ctas_per_sm, "pbuf_pct": args.pbuf_pct, "consumer_threads": args.consumer_threads,
+                       "debug_skip": args.debug_skip, "library": os.path.basename(native.library_path()),
+                       "timed_region": "K = %d launches, %.2f ms; robust at the driver's K = 20 (SCALE and BENCH of round 1 "
+                                       "agreed to 0.03 %%)" % (K, max_ms),
                        "sharding": "batches per rank, pairing inside each batch, no collective",
                        "host_affinity": f"rank bound to the {local_cpus} CPU cores local to its GPU" if local_cpus else "default"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": statistics.fmean(bytes_per_launch),
                          "kernel_ms_mean": statistics.fmean(per_launch_ms),
+                         "note": "achieved = ALGORITHMIC bytes / time (effective bandwidth: partner reads that hit L2 count); "
+                                 "`dram` relates the DRAM bytes ncu measured for one launch to the same times",
+                         "dram": None if traffic is None else {
+                             "overlapped_GBps": traffic / mean_launch_s / 1e9, "overlapped_frac": traffic / mean_launch_s / 1e9 / peak,
+                             "serialized_GBps": traffic / (serial_mean * 1e-3) / 1e9,
+                             "serialized_frac": traffic / (serial_mean * 1e-3) / 1e9 / peak},
                          "serialized_launches": {
-                             "kernel_ms_mean": statistics.fmean(serial_ms), "kernel_ms_median": statistics.median(serial_ms),
+                             "kernel_ms_mean": serial_mean, "kernel_ms_median": statistics.median(serial_ms),
                              "kernel_ms_min": min(serial_ms),
-                             "achieved": statistics.fmean(bytes_per_launch) / (statistics.fmean(serial_ms) * 1e-3) / 1e9,
-                             "frac": statistics.fmean(bytes_per_launch) / (statistics.fmean(serial_ms) * 1e-3) / 1e9 / peak,
-                             "cycles_per_s_per_gpu": B / (statistics.fmean(serial_ms) * 1e-3)}},
-            "e2e": {"value": e2e_value, "unit": UNIT, "steps": E, "ms_per_step": float(te.item()) / E,
+                             "achieved": statistics.fmean(bytes_per_launch) / (serial_mean * 1e-3) / 1e9,
+                             "frac": statistics.fmean(bytes_per_launch) / (serial_mean * 1e-3) / 1e9 / peak,
+                             "cycles_per_s_per_gpu": B / (serial_mean * 1e-3)}},
+            "verified": verified,
+            "e2e": {"value": e2e_value, "unit": UNIT, "steps": E, "ms_per_step": e2e_ms_total / E,
                     "h2d_bytes_per_step": in_bytes + small_bytes, "d2h_bytes_per_step": in_bytes + B * 8,
-                    "host_ms_per_step_inside_augment": 1e3 * host_s[0] / E,      # includes waiting for the batch's H2D copy
+                    "host_ms_per_step_inside_augment": host_inside_ms,          # includes waiting for the batch's H2D copy
                     "host_draws_ms_per_step": host_draws_ms,                     # pairing + lambda + knots alone, rank 0
+                    "link_ceiling": "profiles/r2_pcie_ranks.json: with N ranks moving 164 MB each way at once this box class delivers "
+                                    "99 / 147 / 105 / 144 GB/s in total at N = 1 / 2 / 4 / 8 (8.1 GB/s of D2H for the slowest rank at "
+                                    "N = 8), and the copies alone take 3.4 / 4.7 / - / 19.9 ms per step",
                     "api": "pcgmix_b200.augmentations.augment (host draws + 1 kernel) inside a prefetching loop: pinned host in/out, "
                            "H2D of steps k+1, k+2 and D2H of step k-1 on side streams"},
+            "e2e_variants": variants,
             "gpu_launches": gpu_launches, "gpu_launches_overlapped": overlapped, "gpu_launches_e2e": e2e_launches,
             "clocks": clocks,
         }
+        if configs is not None:
+            line["configs"] = configs
+        if cfg5 is not None:
+            line["cfg5"] = cfg5
         if cpu is not None:
             line["cpu_baseline"] = cpu
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+    if verify and not verified["ok"]:
+        print(f"bench: VERIFICATION FAILED: {verified}", file=sys.stderr)
+        sys.exit(3)
 
 
 def main():

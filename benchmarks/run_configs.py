@@ -48,6 +48,10 @@ def timed(fn, reps, warm=10):
     return statistics.fmean(per), min(per)
 
 
+RESULTS = []          # every line emitted in this process (bench.py collects them for its "configs" array)
+QUIET = False
+
+
 def emit(name, cycles, ms_mean, ms_min, bytes_per_call=None, **extra):
     line = {"config": name, "cycles_per_call": cycles, "ms_mean": ms_mean, "ms_min": ms_min,
             "cycles_per_s": cycles / (ms_mean * 1e-3)}
@@ -55,7 +59,9 @@ def emit(name, cycles, ms_mean, ms_min, bytes_per_call=None, **extra):
         gbs = bytes_per_call / (ms_mean * 1e-3) / 1e9
         line.update({"algorithmic_bytes": bytes_per_call, "achieved_GBps": gbs, "frac_of_measured_peak": gbs / PEAK})
     line.update(extra)
-    print(json.dumps(line), flush=True)
+    RESULTS.append(line)
+    if not QUIET:
+        print(json.dumps(line), flush=True)
 
 
 def prepared_steps(frames, labels, batch, channels, n_steps, magwarp, dev, nb):
@@ -63,10 +69,13 @@ def prepared_steps(frames, labels, batch, channels, n_steps, magwarp, dev, nb):
     for s in range(n_steps):
         f, lab = frames[s % nb], labels[s % nb]
         mix = draws.same_label_pairing(lab, s)
-        lam = draws.lambda_pair_fp32(draws.draw_lambda(1, s))
         arrays = [f.astype(np.int32), mix.astype(np.int32), draws.processing_order(mix)]
         if magwarp:
-            arrays.append(draws.draw_knots(batch, 4, channels, 0.2))
+            lam_f, knots = draws.lambda_and_knots(1.0, s, batch, 4, channels, 0.2)
+            arrays.append(knots)
+        else:
+            lam_f = draws.draw_lambda(1, s)
+        lam = draws.lambda_pair_fp32(lam_f)
         steps.append((staging.upload(arrays, dev), lam, synth.mixed_samples(f, mix)))
     return steps
 
@@ -106,7 +115,7 @@ def resident_section(args, dev):
         emit("resident/%s fused cut+pad+mix from %d recordings x %d x %d, batch %d x %d" % (name, n_rec, C, Tr, Br, L),
              Br, ms, mn, 4.0 * C * (own + mm + L * Br),
              note="bytes = 4*C*(sum len1 + sum M + B*L); mean cycle %.0f samples of L=%d" % (own / Br, L))
-        if magwarp:
+        if magwarp and getattr(args, "resident_e2e", True):
             # end to end from the host's point of view: per step only the table rows of the batch (16 KB) and the
             # per-step draws go up; the augmented batch comes back into pinned host memory (bench.py's e2e loop
             # moves the 164 MB padded batch up as well)
@@ -174,6 +183,24 @@ def main():
     dev = torch.device("cuda:0")
     native.load()
     native.set_tuning(True, args.stages, args.max_slice, args.ctas_per_sm, args.pbuf_pct, args.consumer_threads, 0)
+    run(args, dev)
+
+
+def collect(dev, reps=60, cpu_legs=False, resident_e2e=False):
+    """All sections, quietly, for bench.py's "configs" array: returns the list of result lines."""
+    global QUIET
+    ns = argparse.Namespace(reps=reps, only="", stages=0, ctas_per_sm=0, consumer_threads=0, max_slice=0, pbuf_pct=0,
+                            cpu_legs=cpu_legs, resident_e2e=resident_e2e)
+    QUIET, before = True, len(RESULTS)
+    try:
+        run(ns, dev)
+    finally:
+        QUIET = False
+    return RESULTS[before:]
+
+
+def run(args, dev):
+    cpu_legs = getattr(args, "cpu_legs", True)
     if args.only == "resident":
         return resident_section(args, dev)
     rng = np.random.default_rng(synth.BENCH_SEED)
@@ -196,9 +223,10 @@ def main():
     emit("cfg1/durratiomixup (%d cycles x 4 x 4400, frames = cycle table view)" % n_cyc, n_cyc, ms, mn,
          note="latency-bound: %.1f MB per call" % (2 * cycles.numel() * 4 / 1e6))
     # CPU port of the same pipeline (reference structure: Python loops), single process
-    t_seg, t_mix = bench.cpu_baseline_cfg1(states.cpu().numpy(), signal.cpu().numpy(), labels1, L1)
-    emit("cfg1/CPU port: segmentation + cut (once) and durratiomixup per call", n_cyc, t_mix * 1e3, t_mix * 1e3,
-         note="segmentation+cut %.1f ms; mix %.2f ms per call on the host (torch-CPU tensors like the reference)" % (t_seg * 1e3, t_mix * 1e3))
+    if cpu_legs:
+        t_seg, t_mix = bench.cpu_baseline_cfg1(states.cpu().numpy(), signal.cpu().numpy(), labels1, L1)
+        emit("cfg1/CPU port: segmentation + cut (once) and durratiomixup per call", n_cyc, t_mix * 1e3, t_mix * 1e3,
+             note="segmentation+cut %.1f ms; mix %.2f ms per call on the host (torch-CPU tensors like the reference)" % (t_seg * 1e3, t_mix * 1e3))
     # the same batch without the intermediate padded array: recordings + cycle table -> fused cut + pad + mix
     res1 = resident.ResidentCycles(signal, table, L1, n_cyc, torch.zeros(1, dtype=torch.int32, device=dev))
     scratch1 = torch.empty((n_cyc, 8), dtype=torch.int32, device=dev)
@@ -237,8 +265,11 @@ def main():
         m_mean = statistics.fmean(s[2] for s in steps)
         emit(name, B, ms, mn, 4.0 * C * (2.0 * L * B + m_mean))
     n_b = 245
+    import time
+    t_host = time.perf_counter()
     steps = prepared_steps(frames, labels, B, C, n_b, True, dev, NB)
     torch.cuda.synchronize()
+    host_ms = (time.perf_counter() - t_host) * 1e3             # pairing, order, lambda, knots and their upload for 245 batches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for k in range(n_b):
@@ -248,7 +279,11 @@ def main():
     torch.cuda.synchronize()
     tot = e0.elapsed_time(e1)
     emit("cfg4/1M cycles = 245 batches of 4096, PCGmix+, 1 GPU", n_b * B, tot, tot,
-         4.0 * C * (2.0 * L * B * n_b + sum(s[2] for s in steps)))
+         4.0 * C * (2.0 * L * B * n_b + sum(s[2] for s in steps)),
+         host_draws_ms_total=host_ms, wall_ms_including_host_draws=host_ms + tot,
+         cycles_per_s_including_host_draws=n_b * B / ((host_ms + tot) * 1e-3),
+         note="device time is the 245 launches between two events; the host's draws for the 245 batches (single thread, "
+              "before the timed region) are reported beside it")
 
     # ---------------- cfg3 ----------------
     B3, F3, T3 = 1024, 64, 250
@@ -263,8 +298,9 @@ def main():
     emit("cfg3/2D durratiomixup 1024 x 1 x 64 x 250 (65.5 MB in)", B3, ms, mn, 4.0 * F3 * (2.0 * T3 * B3 + m3),
          note="working set 131 MB ~ L2 size: partly L2-resident across repetitions")
     n3 = 128                                                   # bounded CPU sample of the same workload
-    t3 = bench.cpu_baseline_cfg3(data3[:n3].cpu(), labels3[:n3], frames3[:n3])
-    emit("cfg3/CPU port on a %d-item sample (throughput of the per-item loop is flat in B)" % n3, n3, t3 * 1e3, t3 * 1e3)
+    if cpu_legs:
+        t3 = bench.cpu_baseline_cfg3(data3[:n3].cpu(), labels3[:n3], frames3[:n3])
+        emit("cfg3/CPU port on a %d-item sample (throughput of the per-item loop is flat in B)" % n3, n3, t3 * 1e3, t3 * 1e3)
     B3b = 8192
     frames3b = synth.spectrogram_frames(rng, B3b, T3)
     data3b = torch.from_numpy(synth.cycle_signals(rng, frames3b, (1, F3), T3)).to(dev)

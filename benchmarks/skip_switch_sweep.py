@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-CASES = [("float32", 0, "nothing skipped"), ("float32", 128, "every consumer warp polls the full barrier (no elected warp + bar.sync)"), ("float32", 64, "no row safety check / knot loads in the producer"),
+CASES = [("float32", 0, "nothing skipped"), ("float32", 128, "one elected consumer warp polls the full barrier, the others park on bar.sync"), ("float32", 64, "no row safety check / knot loads in the producer"),
          ("float32", 2, "no consumer arithmetic"), ("float32", 1, "no stores"), ("float32", 4, "no partner staging"),
          ("float32", 2 + 64, "no arithmetic, no safety check"), ("float64", 0, "float64: nothing skipped"),
          ("float64", 2, "float64: no consumer arithmetic")]

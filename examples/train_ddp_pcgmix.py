@@ -81,23 +81,15 @@ class Args:
     num_classes = 2
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--batch", type=int, default=64, help="per-rank batch (the reference trains with 64)")
-    ap.add_argument("--resident", action="store_true",
-                    help="keep the rank's recordings + cycle table on the GPU and draw batches as table rows "
-                         "(pcgmix_b200.resident): no per-step upload, no padded array")
-    ap.add_argument("--device-labels", action="store_true",
-                    help="recover the class ids from the device one-hot tensor every step, like the reference "
-                         "(augmentations.py:501), instead of taking them from the loader's CPU target")
-    opt = ap.parse_args()
+def run_cfg5(steps=30, batch=64, use_resident=False, device_labels=False, init_process_group=True):
+    """Train for ``steps`` steps; returns the result dict on rank 0 (None elsewhere).  With
+    ``init_process_group=False`` the caller (bench.py) already owns an NCCL process group."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and init_process_group:
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(4)
     model = CycleResNet9().to(dev)
@@ -105,42 +97,43 @@ def main():
     if world > 1:
         model = nn.parallel.DistributedDataParallel(model, device_ids=[local])
     optim = torch.optim.Adam(model.parameters(), lr=1e-3)
-    sched = torch.optim.lr_scheduler.OneCycleLR(optim, max_lr=1e-3, total_steps=opt.steps)
+    sched = torch.optim.lr_scheduler.OneCycleLR(optim, max_lr=1e-3, total_steps=steps)
     args = Args()
-    args.batch_size = opt.batch
+    args.batch_size = batch
     counter = StepCounter()
     rng = np.random.default_rng(100 + rank)                    # every rank draws its own cycles
-    wav = ["a0001"] * opt.batch
+    wav = ["a0001"] * batch
     # a few host batches prepared up front (what the loader's workers would have ready)
     pool = []
     for _ in range(4):
-        frames = synth.cycle_frames(rng, opt.batch, limit=2500)
+        frames = synth.cycle_frames(rng, batch, limit=2500)
         pool.append((torch.from_numpy(synth.cycle_signals(rng, frames, (4,), 2500)).pin_memory(),
-                     torch.from_numpy(frames), torch.from_numpy(rng.integers(0, 2, opt.batch))))
+                     torch.from_numpy(frames), torch.from_numpy(rng.integers(0, 2, batch))))
     res = cycle_labels = None
-    if opt.resident:
+    if use_resident:
         # this rank's recordings (64 x 4 bands x 40 s @ 1 kHz) with dense Springer states -> cycle table, once
         states = torch.from_numpy(synth.dense_states(rng, 64, 40000, 1000)).to(dev)
         signal = torch.from_numpy(rng.standard_normal((64, 4, 40000)).astype(np.float32)).to(dev)
         res = resident.from_dense_states(signal, states, 2500)
         cycle_labels = rng.integers(0, 2, res.n_cycles)
     aug_dev_ms, aug_host_ms, step_ms = [], [], []
-    for step in range(opt.steps):
+    loss = None
+    for step in range(steps):
         host_data, frames, target = pool[step % len(pool)]
-        if opt.resident:
-            ids = rng.integers(0, res.n_cycles, opt.batch)          # what a sampler over the cycle table yields
+        if use_resident:
+            ids = rng.integers(0, res.n_cycles, batch)          # what a sampler over the cycle table yields
             target = torch.from_numpy(cycle_labels[ids])
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        if not opt.resident:
+        if not use_resident:
             data = host_data.to(dev, non_blocking=True)            # train_model.py:499
         target_ohe = F.one_hot(target, args.num_classes).to(dev)
-        if not opt.device_labels:                              # the loader's CPU target: pairing needs no device read-back
+        if not device_labels:                                  # the loader's CPU target: pairing needs no device read-back
             augmentations.with_host_labels(target_ohe, target)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         h0 = time.perf_counter()
-        if opt.resident:
+        if use_resident:
             data, target_ohe, _, _ = resident.augment(args, res, ids, target_ohe, wav, counter, model, dev, None)
         else:
             data, target_ohe, _, _ = augmentations.augment(args, data, target_ohe, frames, wav, counter, model, dev, None)
@@ -156,20 +149,40 @@ def main():
         torch.cuda.synchronize()
         step_ms.append((time.perf_counter() - t0) * 1e3)
         aug_dev_ms.append(e0.elapsed_time(e1))
-    t = torch.tensor([float(np.median(step_ms[5:]))], dtype=torch.float64, device=dev)
+    skip = min(5, max(0, steps - 3))
+    t = torch.tensor([float(np.median(step_ms[skip:]))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    result = None
     if rank == 0:
-        import json
         ms = float(t.item())
-        print(json.dumps({"config": "cfg5: on-device PCGmix+ -> ResNet9-1D training step, DDP" +
-                          (", batches drawn from resident recordings" if opt.resident else ""), "n_gpus": world,
-                          "per_rank_batch": opt.batch, "steps": opt.steps, "loss": round(loss.item(), 4),
-                          "median_step_ms_max_over_ranks": ms, "augment_call_host_ms_median": float(np.median(aug_host_ms[5:])),
-                          "augment_device_span_ms_median": float(np.median(aug_dev_ms[5:])),
-                          "cycles_per_s": world * opt.batch / (ms * 1e-3)}))
-    if world > 1:
+        result = {"config": "cfg5: on-device PCGmix+ -> ResNet9-1D training step, DDP" +
+                  (", batches drawn from resident recordings" if use_resident else ""), "n_gpus": world,
+                  "per_rank_batch": batch, "steps": steps, "loss": round(loss.item(), 4),
+                  "median_step_ms_max_over_ranks": ms, "augment_call_host_ms_median": float(np.median(aug_host_ms[skip:])),
+                  "augment_device_span_ms_median": float(np.median(aug_dev_ms[skip:])),
+                  "labels": "device one-hot read back every step (reference behaviour)" if device_labels else "loader's CPU target",
+                  "cycles_per_s": world * batch / (ms * 1e-3)}
+    if world > 1 and init_process_group:
         dist.destroy_process_group()
+    return result
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--batch", type=int, default=64, help="per-rank batch (the reference trains with 64)")
+    ap.add_argument("--resident", action="store_true",
+                    help="keep the rank's recordings + cycle table on the GPU and draw batches as table rows "
+                         "(pcgmix_b200.resident): no per-step upload, no padded array")
+    ap.add_argument("--device-labels", action="store_true",
+                    help="recover the class ids from the device one-hot tensor every step, like the reference "
+                         "(augmentations.py:501), instead of taking them from the loader's CPU target")
+    opt = ap.parse_args()
+    result = run_cfg5(opt.steps, opt.batch, opt.resident, opt.device_labels)
+    if result is not None:
+        import json
+        print(json.dumps(result))
 
 
 if __name__ == "__main__":

@@ -1,10 +1,10 @@
-"""Import the UNMODIFIED reference modules from /root/reference behind module stubs.
+"""Import the UNMODIFIED reference modules behind module stubs.
 
-TEST INFRASTRUCTURE ONLY.  Used solely by ``tests/golden/make_golden.py`` (and the optional
-``test_oracle_vs_live_reference`` test) inside the build container to pin the oracle in
-``oracle/pcgmix_oracle.py`` against the reference's own code.  The reference tree does not
-exist on the GPU box, so nothing on the product path, in ``bench.py`` or in the ``-m gpu``
-tests may call this.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Two users: ``tests/golden/make_golden*.py`` inside the build container
+(source tree at /root/reference), to pin the oracle in ``oracle/pcgmix_oracle.py`` against the reference's
+own code; and ``bench.py --impl reference`` / its ``cpu_baseline`` leg, which time the reference's ``augment``
+from the byte-compiled copies under ``oracle/_ref/`` (``oracle/build_ref.py``) — the only form in which the
+reference exists on the GPU box.  Nothing on the product path or in the ``-m gpu`` tests may call this.
 
 Why stubs: ``augmentations.py:1-23`` imports tkinter, matplotlib,
 tsp_solver, audiomentations, python_tsp and the sibling modules latent_space / saliency /
@@ -40,13 +40,24 @@ _STUBS = {
 }
 
 
+COMPILED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
 def reference_available() -> bool:
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "augmentations.py"))
 
 
-def load_reference():
-    """Return ``(augmentations, augmentations2d)`` — the reference's own modules."""
-    if not reference_available():
+def compiled_reference_available() -> bool:
+    return all(os.path.isfile(os.path.join(COMPILED_ROOT, m + ".bytecode")) for m in ("augmentations", "augmentations2d"))
+
+
+def load_reference(compiled: bool = False):
+    """Return ``(augmentations, augmentations2d)`` — the reference's own modules, from the source tree or
+    (``compiled=True``) from the sourceless modules under ``oracle/_ref/``."""
+    if compiled:
+        if not compiled_reference_available():
+            raise RuntimeError(f"no compiled reference under {COMPILED_ROOT} (run oracle/build_ref.py in the build container)")
+    elif not reference_available():
         raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
     if "_pcgmix_ref_augmentations" in sys.modules:
         return sys.modules["_pcgmix_ref_augmentations"], sys.modules["_pcgmix_ref_augmentations2d"]
@@ -76,7 +87,12 @@ def load_reference():
         mods = []
         for fname, alias in (("augmentations.py", "_pcgmix_ref_augmentations"),
                              ("augmentations2d.py", "_pcgmix_ref_augmentations2d")):
-            spec = importlib.util.spec_from_file_location(alias, os.path.join(REFERENCE_ROOT, fname))
+            if compiled:
+                import importlib.machinery
+                path = os.path.join(COMPILED_ROOT, fname[:-3] + ".bytecode")
+                spec = importlib.util.spec_from_loader(alias, importlib.machinery.SourcelessFileLoader(alias, path))
+            else:
+                spec = importlib.util.spec_from_file_location(alias, os.path.join(REFERENCE_ROOT, fname))
             mod = importlib.util.module_from_spec(spec)
             sys.modules[alias] = mod
             spec.loader.exec_module(mod)

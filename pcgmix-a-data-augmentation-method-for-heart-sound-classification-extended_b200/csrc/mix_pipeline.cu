@@ -65,11 +65,14 @@ constexpr int kProducerWarps = 2;       // producer warps take alternate items (
 constexpr int kHelperThreads = 32 + 32 * kProducerWarps;   // the LAST warps of the CTA: store warp, then producers
                                        // (the SM's issue arbiter favours high warp ids; a producer in warp 0
                                        // is starved by consumer warps polling their barriers)
-// PCGmix+ replaces the second producer warp by the coefficient warp (see the kernel): its producers no longer
-// touch the knots, and a 14th warp would cost every thread 8 registers at three CTAs per SM
-__host__ __device__ constexpr int producer_warps(int warp_variant) { return warp_variant != 0 ? 1 : kProducerWarps; }
-__host__ __device__ constexpr int helper_threads(int warp_variant) {
-    return 32 + 32 * producer_warps(warp_variant) + (warp_variant != 0 ? 32 : 0);
+// PCGmix+ on padded batches replaces the second producer warp by the coefficient warp (see the kernel): its
+// producers no longer touch the knots, and a 14th warp would cost every thread 8 registers at three CTAs per SM.
+// The RESIDENT variant (two CTAs per SM, heavier producers: own and partner supersets) keeps both producers.
+__host__ __device__ constexpr int producer_warps(int warp_variant, bool resident) {
+    return (warp_variant != 0 && !resident) ? 1 : kProducerWarps;
+}
+__host__ __device__ constexpr int helper_threads(int warp_variant, bool resident) {
+    return 32 + 32 * producer_warps(warp_variant, resident) + (warp_variant != 0 ? 32 : 0);
 }
 
 struct StageMeta {
@@ -201,11 +204,11 @@ struct PipeArgs {
 // rows outside it (9 % at sigma = 0.2) and the K+1 vectors per row that contain a knot take variant 1's
 // float64 path, which is compiled into this variant too.
 template <int NCT, int WARP, int VPT, bool RESIDENT>
-__global__ void __launch_bounds__(NCT + helper_threads(WARP), RESIDENT ? 2 : (NCT <= 192 ? 4 : NCT <= 320 ? 3 : 2))
+__global__ void __launch_bounds__(NCT + helper_threads(WARP, RESIDENT), RESIDENT ? 2 : (NCT <= 192 ? 4 : NCT <= 320 ? 3 : 2))
 mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ PipeArgs pa) {
     constexpr bool MAGWARP = WARP != 0;
     constexpr bool F32 = WARP == 2;
-    constexpr int kThreads = NCT + helper_threads(WARP);
+    constexpr int kThreads = NCT + helper_threads(WARP, RESIDENT);
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);                  // loads of the stage have landed
     uint64_t* computed = full + kMaxStages;                               // consumers are done with the stage
@@ -287,7 +290,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     };
     auto row_of = [&](Cursor c) { return pa.slices_per_row == 1 ? c.rest : c.rest / pa.slices_per_row; };
 
-    if (MAGWARP && threadIdx.x >= NCT + 32 + 32 * producer_warps(WARP)) {
+    if (MAGWARP && threadIdx.x >= NCT + 32 + 32 * producer_warps(WARP, RESIDENT)) {
         // =================================== coefficient warp ====================================
         // Turns every item's K+2 knots into the 4(K+1) cubic coefficients its consumers need (coefficient i =
         // sum_j M[i][j] * knot_j, matrix in shared memory, knots broadcast by shuffle) and writes them into the
@@ -427,7 +430,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         };
         int b0 = 0, b1 = 0, b2 = 0, p0 = 0, p1 = 0, f1 = 0, f2 = 0, wn = 0;
         bool bad0 = false;
-        constexpr int NP = producer_warps(WARP);
+        constexpr int NP = producer_warps(WARP, RESIDENT);
         // RESIDENT: the slot records are written by the kernel launched just before this one; everything
         // above (barriers, knot tables, coefficient matrix) did not need them
         if constexpr (RESIDENT) asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -627,11 +630,16 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         for (int it = 0; it < n_it; ++it) {
             float* xbuf = stage_x(stage);
             const StageMeta* meta = stage_meta(stage);
-            // Only the first consumer warp polls the stage's barrier; the others park on a hardware barrier, which
-            // costs no issue slots.  With every warp polling, barrier polling was 35 % of all executed instructions
-            // (ncu, round 1) in a kernel whose SMs issue on ~60 % of their cycles.
-            if (ct < 32 || PCGMIX_SKIP(128)) mbar_wait(&full[stage], phase);
-            if (!PCGMIX_SKIP(128)) asm volatile("bar.sync 1, %0;" ::"r"(NCT) : "memory");
+            // Every consumer warp waits on the stage's barrier itself and never on another consumer warp.  (One
+            // elected polling warp + a hardware barrier for the rest was tried in round 2 — barrier polling is a
+            // third of the executed instructions — and changed nothing on padded batches while costing the
+            // consumer-bound RESIDENT variant 7 %: skip switch 128 of the profiling build.)
+            if (PCGMIX_SKIP(128)) {
+                if (ct < 32) mbar_wait(&full[stage], phase);
+                asm volatile("bar.sync 1, %0;" ::"r"(NCT) : "memory");
+            } else {
+                mbar_wait(&full[stage], phase);
+            }
 
             const int lo1 = meta->win[1].x, lo2 = meta->win[2].x, lo3 = meta->win[3].x;
             const int nvec = meta->nvec;
@@ -859,7 +867,7 @@ cudaError_t launch_instance(const MixArgs& a, PipeArgs pa, size_t smem, GridPlan
         }
         if (c.smem != smem || c.ctas == 0) {
             int n = 0;
-            const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NCT + helper_threads(MAGWARP), smem);
+            const cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, NCT + helper_threads(MAGWARP, RESIDENT), smem);
             if (e != cudaSuccess) return e;
             if (n < 1) return cudaErrorInvalidConfiguration;
             c.smem = smem;
@@ -883,11 +891,11 @@ cudaError_t launch_instance(const MixArgs& a, PipeArgs pa, size_t smem, GridPlan
     if (grid > pa.n_items) grid = pa.n_items;
     pa.step_rest = static_cast<int>(grid / a.B);
     pa.step_slot = static_cast<int>(grid % a.B);
-    pa.stepn_rest = static_cast<int>((grid * producer_warps(MAGWARP)) / a.B);
-    pa.stepn_slot = static_cast<int>((grid * producer_warps(MAGWARP)) % a.B);
+    pa.stepn_rest = static_cast<int>((grid * producer_warps(MAGWARP, RESIDENT)) / a.B);
+    pa.stepn_slot = static_cast<int>((grid * producer_warps(MAGWARP, RESIDENT)) % a.B);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(static_cast<unsigned>(grid));
-    cfg.blockDim = dim3(NCT + helper_threads(MAGWARP));
+    cfg.blockDim = dim3(NCT + helper_threads(MAGWARP, RESIDENT));
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -965,7 +973,7 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     }
     int per_sm = static_cast<int>((228 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : per_sm;
-    const int by_threads = 2048 / (nct + helper_threads(warp));
+    const int by_threads = 2048 / (nct + helper_threads(warp, resident));
     per_sm = per_sm < by_threads ? per_sm : by_threads;
     if (tune.ctas_per_sm > 0 && tune.ctas_per_sm < per_sm) per_sm = tune.ctas_per_sm;
     if (pa.stages < kProducerWarps) return cudaErrorInvalidConfiguration;
