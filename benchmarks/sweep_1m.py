@@ -11,13 +11,17 @@ depend on N; there is no collective on the path (NCCL only carries the barrier a
 ranks).  All of a rank's batches are resident in its HBM (40 GB at N = 1); the signals are drawn on
 the device (the values do not matter for the timing, the offsets and labels are drawn like in
 bench.py), host draws are uploaded before the timed region, consecutive launches may overlap.
-One JSON line per run.
+The host's share — pairing, processing order, lambda and knots of the rank's batches, drawn by the native replay
+on a few worker threads (it releases the GIL), and their upload — is timed on the wall clock and reported beside
+the device time (``host_draws_seconds``, ``seconds_including_host_draws``).  One JSON line per run.
 """
 from __future__ import annotations
 
 import json
 import os
 import sys
+import time
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 import torch
@@ -43,6 +47,7 @@ def main():
     gen = torch.Generator(device=dev)
     data, metas, m_total = [], [], 0
     t = torch.arange(L, device=dev)[None, None, :]
+    inputs = []
     for k in mine:
         rng = np.random.default_rng(synth.BENCH_SEED + k)
         frames = synth.cycle_frames(rng, B, limit=L)
@@ -50,14 +55,26 @@ def main():
         gen.manual_seed(k)
         x = torch.randn((B, C, L), device=dev, generator=gen)
         x *= (t < torch.from_numpy(frames[:, 4]).to(dev)[:, None, None])
-        seed = sharding.step_seed(k)
-        mix = draws.same_label_pairing(labels, seed)
-        lam = draws.lambda_pair_fp32(draws.draw_lambda(1, seed))
-        up = staging.upload([frames.astype(np.int32), mix.astype(np.int32), draws.processing_order(mix),
-                             draws.draw_knots(B, KNOT, C, SIGMA)], dev)
         data.append(x)
-        metas.append((up, lam))
+        inputs.append((frames, labels, sharding.step_seed(k)))
+    torch.cuda.synchronize()
+
+    def host_draws(item):                                      # everything the host contributes to one batch
+        frames, labels, seed = item
+        mix = draws.same_label_pairing(labels, seed)
+        lam, knots = native.host_lambda_knots(seed, 1.0, SIGMA, (B, KNOT + 2, C), max_threads=1, want_state=False)
+        return mix, draws.processing_order(mix), lam, knots
+
+    workers = max(1, min(8, (os.cpu_count() or 1) // max(world, 1)))
+    t_host = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        drawn = list(pool.map(host_draws, inputs))
+    for (frames, labels, seed), (mix, order, lam, knots) in zip(inputs, drawn):
+        up = staging.upload([frames.astype(np.int32), mix.astype(np.int32), order, knots], dev)
+        metas.append((up, draws.lambda_pair_fp32(lam)))
         m_total += synth.mixed_samples(frames, mix)
+    torch.cuda.synchronize()
+    host_seconds = time.perf_counter() - t_host
     outs = [torch.empty((B, C, L), device=dev) for _ in range(3)]
 
     prepared = [augmentations.prepare_on_device(data[i], up[0], up[1], lam[0], lam[1], outs[i % 3], up[3], KNOT,
@@ -81,6 +98,9 @@ def main():
     torch.cuda.synchronize()
     native.set_launch_overlap(False)
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    host_s = torch.tensor([host_seconds], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(host_s, op=dist.ReduceOp.MAX)
     bytes_local = torch.tensor([4.0 * C * (2.0 * L * B * len(mine) + m_total)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -96,6 +116,9 @@ def main():
         print(json.dumps({"config": "cfg4: 1M cycles = 245 batches of 4096 x 4 x 2500, durmixmagwarp(0.2,4)",
                           "n_gpus": world, "cycles": N_BATCHES * B, "seconds": sec, "cycles_per_s": N_BATCHES * B / sec,
                           "aggregate_algorithmic_GBps": gbs, "frac_of_measured_peak_per_gpu": gbs / world / peak,
+                          "host_draws_seconds": float(host_s.item()), "host_draw_threads_per_rank": workers,
+                          "seconds_including_host_draws": sec + float(host_s.item()),
+                          "cycles_per_s_including_host_draws": N_BATCHES * B / (sec + float(host_s.item())),
                           "sharding": "batch k -> rank k mod N, seed k, no collective"}))
     if world > 1:
         dist.destroy_process_group()

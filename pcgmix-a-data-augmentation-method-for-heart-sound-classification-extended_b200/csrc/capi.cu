@@ -216,7 +216,7 @@ int pcgmix_set_tuning(int32_t use_pipeline, int32_t stages, int32_t max_slice, i
     if (debug & 0xffdf) return fail("the skip switches exist only in a library built with -DPCGMIX_PROFILING");
     g_tuning.debug = debug & 32;
 #endif
-    g_tuning.vec_per_thread = 0;
+
     return 0;
 }
 
@@ -232,6 +232,14 @@ int pcgmix_get_spline_precision(void) {
 }
 
 long long pcgmix_overlap_launches(void) { return g_overlap_launches; }
+
+#ifdef PCGMIX_PROFILING
+// profiling build only: per-CTA {start, first item consumed, last store done} (globaltimer ns) of the last pipelined launch
+int pcgmix_debug_timeline(unsigned long long* host, int32_t n_ctas) {
+    const cudaError_t e = pcgmix::read_timeline(host, n_ctas);
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_debug_timeline", e);
+}
+#endif
 
 int pcgmix_set_launch_overlap(int32_t enable) {
     std::lock_guard<std::mutex> lock(g_overlap_mutex);

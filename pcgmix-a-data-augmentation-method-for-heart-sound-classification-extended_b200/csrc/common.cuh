@@ -117,6 +117,10 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
                                 unsigned long long previous_signature, cudaStream_t stream,
                                 unsigned long long* full_grid_signature);
 
+#ifdef PCGMIX_PROFILING
+cudaError_t read_timeline(unsigned long long* host, int n_ctas);   // mix_pipeline.cu, profiling build only
+#endif
+
 // segment_kernels.cu
 cudaError_t launch_segment_dense(const int8_t* states, int32_t R, int32_t T, int32_t downsample,
                                  int32_t* cycles, int32_t max_cycles, int32_t* cycle_count,

@@ -58,6 +58,16 @@ namespace {
 #define PCGMIX_SKIP(bit) false
 #endif
 
+#ifdef PCGMIX_PROFILING
+// per-CTA {first instruction, first item consumed, last store done} in globaltimer nanoseconds, last launch only
+__device__ unsigned long long g_timeline[3 * 2048];
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 constexpr int kMaxStages = 8;
 constexpr int kHeaderBytes = 1024;
 constexpr int kProducerWarps = 2;       // producer warps take alternate items (one warp's instruction stream per
@@ -237,6 +247,9 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         next = warm(a.windows, static_cast<long long>(a.B) * 48, next);
         if constexpr (MAGWARP) next = warm(a.knots, static_cast<long long>(a.B) * (a.K + 2) * a.R * 8, next);
     }
+#ifdef PCGMIX_PROFILING
+    if (threadIdx.x == 0 && blockIdx.x < 2048) g_timeline[3 * blockIdx.x] = global_ns();
+#endif
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], MAGWARP ? 2 : 1);      // producer (+ the row's coefficients from the coefficient warp)
@@ -603,6 +616,9 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 }
             }
             bulk_store_wait_all();                         // every result is in global memory before exit
+#ifdef PCGMIX_PROFILING
+            if (blockIdx.x < 2048) g_timeline[3 * blockIdx.x + 2] = global_ns();
+#endif
         }
     } else {
         // ===================================== consumer warps ====================================
@@ -640,6 +656,9 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             } else {
                 mbar_wait(&full[stage], phase);
             }
+#ifdef PCGMIX_PROFILING
+            if (it == 0 && ct == 0 && blockIdx.x < 2048) g_timeline[3 * blockIdx.x + 1] = global_ns();
+#endif
 
             const int lo1 = meta->win[1].x, lo2 = meta->win[2].x, lo3 = meta->win[3].x;
             const int nvec = meta->nvec;
@@ -914,6 +933,12 @@ cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, size_t smem, int wa
 }
 
 }  // namespace
+
+#ifdef PCGMIX_PROFILING
+cudaError_t read_timeline(unsigned long long* host, int n_ctas) {
+    return cudaMemcpyFromSymbol(host, g_timeline, sizeof(unsigned long long) * 3 * static_cast<size_t>(n_ctas > 2048 ? 2048 : n_ctas));
+}
+#endif
 
 bool pipeline_applicable(const MixArgs& a, bool box) {
     const void* src = a.signal != nullptr ? static_cast<const void*>(a.signal) : static_cast<const void*>(a.x);

@@ -349,6 +349,35 @@ def test_pcgmix_plus_large_batch_sampled():
     assert _rel_err(got[sample], want) <= REL_TOL
 
 
+def test_pcgmix_plus_benchmark_size_sampled():
+    """bench.py's exact workload (BASELINE config 2: 4096 cycles x 4 x 2500, pairing-chain order, through the
+    prepared-launch path the benchmark uses) against the oracle on 96 sampled cycles."""
+    from pcgmix_b200 import augmentations, draws, staging, synth
+    rng = np.random.default_rng(synth.BENCH_SEED)
+    b, c, length, step = 4096, 4, 2500, 23
+    frames = synth.cycle_frames(rng, b, fs=1000, limit=length)
+    data = synth.cycle_signals(rng, frames, (c,), length)
+    labels = rng.integers(0, 2, b)
+    dev = torch.device("cuda:0")
+    mix = draws.same_label_pairing(labels, step)
+    lam, knots = draws.lambda_and_knots(1.0, step, b, 4, c, 0.2)
+    lam32, oml = draws.lambda_pair_fp32(lam)
+    up = staging.upload([frames.astype(np.int32), mix.astype(np.int32), draws.processing_order(mix), knots], dev)
+    x = torch.from_numpy(data).to(dev)
+    out = torch.empty_like(x)
+    augmentations.prepare_on_device(x, up[0], up[1], lam32, oml, out, up[3], 4, order_dev=up[2]).launch()
+    torch.cuda.synchronize()
+    assert np.array_equal(mix, orc.same_label_mix_indices(labels, step)) and lam == orc.draw_lambda(1, step)
+    assert np.array_equal(knots, orc.draw_knots(b, 4, c, 0.2))                   # (global stream: right after draw_lambda)
+    sample = np.sort(rng.choice(b, 96, replace=False))
+    mixed = np.stack([orc.mix_pair(data[i], data[mix[i]], frames[i], frames[mix[i]], lam32) for i in sample])
+    want = (mixed.astype(np.float64) * orc.warp_curves(length, knots[sample])).astype(np.float32)
+    got = out[torch.from_numpy(sample).to(dev)].cpu().numpy()
+    assert _rel_err(got, want) <= REL_TOL
+    if _bit_faithful_warp():
+        assert np.mean(got == want) > 0.999
+
+
 @pytest.mark.parametrize("shape", [(7, 4, 2500), (3, 2, 10000), (5, 3, 1001), (4, 1, 64 * 250)])
 @pytest.mark.parametrize("magwarp", [False, True])
 def test_output_guard_bands_stay_intact(shape, magwarp):
