@@ -62,10 +62,13 @@ def main():
     def host_draws(item):                                      # everything the host contributes to one batch
         frames, labels, seed = item
         mix = draws.same_label_pairing(labels, seed)
-        lam, knots = native.host_lambda_knots(seed, 1.0, SIGMA, (B, KNOT + 2, C), max_threads=1, want_state=False)
+        lam, knots, _ = native.host_lambda_knots(seed, 1.0, SIGMA, (B, KNOT + 2, C), max_threads=1, want_state=False)
         return mix, draws.processing_order(mix), lam, knots
 
     workers = max(1, min(8, (os.cpu_count() or 1) // max(world, 1)))
+    host_draws(inputs[0])                                       # (library load, thread start-up: not part of the sweep)
+    staging.upload([np.zeros(16, np.int32)], dev)
+    torch.cuda.synchronize()
     t_host = time.perf_counter()
     with ThreadPoolExecutor(max_workers=workers) as pool:
         drawn = list(pool.map(host_draws, inputs))

@@ -25,7 +25,7 @@ import torch
 
 from . import draws, native, segmentation, staging
 from ._common import labels_from_one_hot
-from .augmentations import _device_tables
+from .augmentations import _SMALL_DRAW, _device_tables, _plan_for
 
 __all__ = ["ResidentCycles", "from_dense_states", "from_state_table", "augment", "mix_rows"]
 
@@ -127,9 +127,9 @@ def augment(args, resident: ResidentCycles, cycle_ids, target_ohe, wav, step_cou
     Returns ``(data_new, target_ohe, mix_indices, None)`` with ``data_new`` (B, C, L) on the device.
     When the method is not a PCGmix one or the probability gate fails the batch is returned
     un-augmented (cut + padded), with ``mix_indices = []`` like the reference (``augmentations.py:938-939``)."""
-    plan = draws.parse_method_1d(args.method)
+    plan = _plan_for(args.method)
     step = step_counter.count
-    if plan is None or draws.gate(step) >= plan.probability:
+    if plan is None or (plan.probability < 1.0 and draws.gate(step) >= plan.probability):
         return resident.padded(cycle_ids), target_ohe, [], None
     if plan.rand_displacement:
         raise NotImplementedError("the (rand) displacement variant needs the offsets on the host; use "
@@ -144,8 +144,13 @@ def augment(args, resident: ResidentCycles, cycle_ids, target_ohe, wav, step_cou
     if plan.branch == "durmixmagwarp":
         if plan.knot > native.MAX_KNOT:
             raise ValueError(f"durmixmagwarp knot={plan.knot} exceeds the supported maximum {native.MAX_KNOT}")
-        lam, knots = draws.lambda_and_knots(plan.alpha, step, batch, plan.knot, resident.channels, plan.sigma)
-        draws.prefetch_lambda_and_knots(plan.alpha, step + 1, batch, plan.knot, resident.channels, plan.sigma)
+        if batch * (plan.knot + 2) * resident.channels <= _SMALL_DRAW:
+            # small draws: NumPy itself (a C call either way, and its global stream ends where the reference leaves it)
+            lam = draws.draw_lambda(plan.alpha, step)
+            knots = draws.draw_knots(batch, plan.knot, resident.channels, plan.sigma)
+        else:
+            lam, knots = draws.lambda_and_knots(plan.alpha, step, batch, plan.knot, resident.channels, plan.sigma)
+            draws.prefetch_lambda_and_knots(plan.alpha, step + 1, batch, plan.knot, resident.channels, plan.sigma)
         uploads.append(knots)
     else:
         lam = draws.draw_lambda(plan.alpha, step)
