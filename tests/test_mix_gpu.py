@@ -474,6 +474,40 @@ def test_launch_overlap_keeps_results_and_respects_dependencies():
         native.set_launch_overlap(False)
 
 
+def test_launch_overlap_bookkeeping_is_reset_by_other_launches_of_the_library(kernel_choice):
+    """A mix launch may only be made a programmatic dependent of another PCGmix launch whose buffers are disjoint —
+    never of the kernel that uploaded its per-step tables (or cut its cycles): every other entry point that launches
+    on the stream resets the bookkeeping.  Counted through `pcgmix_overlap_launches`."""
+    from pcgmix_b200 import native, staging, synth
+    if kernel_choice == "direct":
+        pytest.skip("only pipelined launches overlap")
+    rng = np.random.default_rng(56)
+    b, c, length = 1024, 4, 2500                               # enough items to fill the GPU (overlap needs a full grid)
+    dev = torch.device("cuda:0")
+    frames = synth.cycle_frames(rng, b, limit=length)
+    f = torch.from_numpy(frames.astype(np.int32)).to(dev)
+    x = [torch.from_numpy(synth.cycle_signals(rng, frames, (c,), length)).to(dev) for _ in range(3)]
+    outs = [torch.empty_like(x[0]) for _ in range(3)]
+    mix = torch.from_numpy(rng.permutation(b).astype(np.int32)).to(dev)
+    lam = np.float32(0.4)
+    native.set_launch_overlap(True)
+    try:
+        native.mix1d(x[0], outs[0], f, mix, lam, np.float32(1) - lam)
+        before = native.overlap_launches()
+        native.mix1d(x[1], outs[1], f, mix, lam, np.float32(1) - lam)        # disjoint from the previous launch: overlapped
+        assert native.overlap_launches() == before + 1
+        up = staging.upload([frames.astype(np.int32)], dev)                  # the library's own table upload on the same stream
+        native.mix1d(x[2], outs[2], up[0], mix, lam, np.float32(1) - lam)    # reads what that upload wrote: ordinary stream order
+        assert native.overlap_launches() == before + 1
+        native.mix1d(x[0], outs[0], f, mix, lam, np.float32(1) - lam)        # and the launch after it may overlap again
+        assert native.overlap_launches() == before + 2
+        torch.cuda.synchronize()
+        want = orc.mix_batch(x[2].cpu().numpy(), frames, mix.cpu().numpy(), lam)
+        assert np.array_equal(outs[2].cpu().numpy().view(np.uint32), want.view(np.uint32))
+    finally:
+        native.set_launch_overlap(False)
+
+
 def test_prepared_launch_matches_plain_call():
     from pcgmix_b200 import augmentations, draws, native, synth
     rng = np.random.default_rng(91)
