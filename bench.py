@@ -463,7 +463,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from pcgmix_b200 import augmentations, draws, native, resident, spline, staging, synth
+    from pcgmix_b200 import augmentations, draws, native, resident, staging, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -25,7 +25,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 sys.path.insert(0, ROOT)
 
 import bench  # noqa: E402  (the CPU-baseline legs live in bench.py: the only non-test code that may run oracle/)
-from pcgmix_b200 import augmentations, draws, native, resident, segmentation, spline, staging, synth  # noqa: E402
+from pcgmix_b200 import augmentations, draws, native, resident, segmentation, staging, synth  # noqa: E402
 
 PEAK = 6544.7
 try:

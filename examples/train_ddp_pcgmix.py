@@ -81,7 +81,7 @@ class Args:
     num_classes = 2
 
 
-def run_cfg5(steps=30, batch=64, use_resident=False, device_labels=False, init_process_group=True):
+def run_cfg5(steps=30, batch=64, use_resident=False, device_labels=False, init_process_group=True, sync_every_step=False):
     """Train for ``steps`` steps; returns the result dict on rank 0 (None elsewhere).  With
     ``init_process_group=False`` the caller (bench.py) already owns an NCCL process group."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -116,15 +116,26 @@ def run_cfg5(steps=30, batch=64, use_resident=False, device_labels=False, init_p
         signal = torch.from_numpy(rng.standard_normal((64, 4, 40000)).astype(np.float32)).to(dev)
         res = resident.from_dense_states(signal, states, 2500)
         cycle_labels = rng.integers(0, 2, res.n_cycles)
-    aug_dev_ms, aug_host_ms, step_ms = [], [], []
+    # Timing: like a real loop, nothing waits for the GPU inside a step; the host runs at most two steps ahead (it waits
+    # for step k-2 at the top of step k, as a loader / logging call would make it), the device is synchronised once
+    # after the warm-up steps and once at the end, and the step time is the wall clock of the steps in between divided
+    # by their number.  ``sync_every_step`` restores a synchronisation per step.
+    warm = min(5, max(0, steps - 3))
+    aug_events, aug_host_ms, step_done = [], [], []
     loss = None
+    t_begin = None
     for step in range(steps):
+        if step >= 2 and not sync_every_step:
+            step_done[step - 2].synchronize()                  # the host stays at most two steps ahead of the device
+        if step == warm:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t_begin = time.perf_counter()
         host_data, frames, target = pool[step % len(pool)]
         if use_resident:
             ids = rng.integers(0, res.n_cycles, batch)          # what a sampler over the cycle table yields
             target = torch.from_numpy(cycle_labels[ids])
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
         if not use_resident:
             data = host_data.to(dev, non_blocking=True)            # train_model.py:499
         target_ohe = F.one_hot(target, args.num_classes).to(dev)
@@ -137,8 +148,10 @@ def run_cfg5(steps=30, batch=64, use_resident=False, device_labels=False, init_p
             data, target_ohe, _, _ = resident.augment(args, res, ids, target_ohe, wav, counter, model, dev, None)
         else:
             data, target_ohe, _, _ = augmentations.augment(args, data, target_ohe, frames, wav, counter, model, dev, None)
-        aug_host_ms.append((time.perf_counter() - h0) * 1e3)
+        if step >= warm:
+            aug_host_ms.append((time.perf_counter() - h0) * 1e3)
         e1.record()
+        aug_events.append((e0, e1))
         loss = F.cross_entropy(model(data), target_ohe.float().argmax(1))
         loss.backward()                                        # DDP all-reduces the gradients over NCCL here
         nn.utils.clip_grad_value_(model.parameters(), 0.1)
@@ -146,11 +159,15 @@ def run_cfg5(steps=30, batch=64, use_resident=False, device_labels=False, init_p
         optim.zero_grad(set_to_none=True)
         sched.step()
         counter.add()
-        torch.cuda.synchronize()
-        step_ms.append((time.perf_counter() - t0) * 1e3)
-        aug_dev_ms.append(e0.elapsed_time(e1))
-    skip = min(5, max(0, steps - 3))
-    t = torch.tensor([float(np.median(step_ms[skip:]))], dtype=torch.float64, device=dev)
+        done = torch.cuda.Event()
+        done.record()
+        step_done.append(done)
+        if sync_every_step:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    step_ms_mean = (time.perf_counter() - t_begin) * 1e3 / max(1, steps - warm)
+    aug_dev_ms = [a.elapsed_time(b) for a, b in aug_events[warm:]]
+    t = torch.tensor([step_ms_mean], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     result = None
@@ -159,8 +176,10 @@ def run_cfg5(steps=30, batch=64, use_resident=False, device_labels=False, init_p
         result = {"config": "cfg5: on-device PCGmix+ -> ResNet9-1D training step, DDP" +
                   (", batches drawn from resident recordings" if use_resident else ""), "n_gpus": world,
                   "per_rank_batch": batch, "steps": steps, "loss": round(loss.item(), 4),
-                  "median_step_ms_max_over_ranks": ms, "augment_call_host_ms_median": float(np.median(aug_host_ms[skip:])),
-                  "augment_device_span_ms_median": float(np.median(aug_dev_ms[skip:])),
+                  "step_ms_max_over_ranks": ms, "augment_call_host_ms_median": float(np.median(aug_host_ms)),
+                  "augment_device_span_ms_median": float(np.median(aug_dev_ms)),
+                  "timing": ("device synchronised every step" if sync_every_step else
+                             "wall clock of steps %d..%d / their number, one synchronisation at each end" % (warm, steps - 1)),
                   "labels": "device one-hot read back every step (reference behaviour)" if device_labels else "loader's CPU target",
                   "cycles_per_s": world * batch / (ms * 1e-3)}
     if world > 1 and init_process_group:
@@ -178,8 +197,9 @@ def main():
     ap.add_argument("--device-labels", action="store_true",
                     help="recover the class ids from the device one-hot tensor every step, like the reference "
                          "(augmentations.py:501), instead of taking them from the loader's CPU target")
+    ap.add_argument("--sync-every-step", action="store_true", help="synchronise the device after every step (round-1 timing)")
     opt = ap.parse_args()
-    result = run_cfg5(opt.steps, opt.batch, opt.resident, opt.device_labels)
+    result = run_cfg5(opt.steps, opt.batch, opt.resident, opt.device_labels, sync_every_step=opt.sync_every_step)
     if result is not None:
         import json
         print(json.dumps(result))

@@ -266,8 +266,10 @@ def lambda_and_knots(alpha: float, step: int, batch: int, knot: int, channels: i
 
 
 def lambda_pair_fp32(lam: float):
-    """``(lam32, 1 - lam32)`` rounded the way the reference's float32 tensor expression rounds."""
-    lam32 = np.array(np.ones(1) * lam).astype("float32")[0]
+    """``(lam32, 1 - lam32)`` rounded the way the reference's float32 tensor expression rounds: lambda is stored in a
+    float32 array (``np.array(np.ones(B) * lam).astype('float32')``, augmentations.py:962-963 — one rounding of the
+    float64 value to nearest) and ``1 - lams`` is evaluated in float32."""
+    lam32 = np.float32(lam)
     return lam32, np.float32(1) - lam32
 
 

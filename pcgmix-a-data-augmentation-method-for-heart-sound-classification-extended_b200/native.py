@@ -203,6 +203,16 @@ def copy_small(dst, src, nbytes: int):
     launch_count += 1 if nbytes > 0 else 0
 
 
+def copy_small_raw(dst_ptr: int, src_ptr: int, nbytes: int, device):
+    """``copy_small`` for callers that own both buffers (the staging ring): no tensor checks, raw addresses."""
+    global launch_count
+    with _on_device(device):
+        rc = load().pcgmix_copy_small(dst_ptr, src_ptr, int(nbytes), _stream_handle(device))
+    if rc != 0:
+        _check(rc, "pcgmix_copy_small")
+    launch_count += 1 if nbytes > 0 else 0
+
+
 def host_group_permutation(group_ids, n_groups: int, seed: int):
     """``mix[idx_g] = random.Random(seed).sample(idx_g, len(idx_g))`` for every group, computed by
     the C++ replay of CPython's algorithm (host code, no GPU involved)."""

@@ -51,10 +51,13 @@ class Uploader:
         """Upload the first ``nbytes`` of a filled slot; returns the device copy (uint8)."""
         nbytes = (max(int(nbytes), _ALIGN) + _ALIGN - 1) // _ALIGN * _ALIGN
         dev_buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        native.copy_small(dev_buf, slot.buf, nbytes)
+        native.copy_small_raw(dev_buf.data_ptr(), slot.buf.data_ptr(), nbytes, device)
         if slot.event is None:
             slot.event = torch.cuda.Event()
-        slot.event.record(torch.cuda.current_stream(device))
+        if device.index is None or device.index == torch.cuda.current_device():
+            slot.event.record()                            # current stream of the current device: no Stream object built
+        else:
+            slot.event.record(torch.cuda.current_stream(device))
         return dev_buf
 
     def upload(self, arrays: Sequence[np.ndarray], device: torch.device) -> List[torch.Tensor]:

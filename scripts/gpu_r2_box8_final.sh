@@ -16,7 +16,7 @@ for n in (8,4):
     try:
         d=json.loads(open(f'gpurun_out/r2_final_bench_{n}gpu.json').read().strip().splitlines()[-1])
         print(n,'value',round(d['value']/1e6,1),'e2e',round(d['e2e']['value']/1e6,3), {k:round(v['value']/1e6,2) for k,v in d['e2e_variants'].items()}, 'verified', d['verified']['ok'])
-        print('  cfg5', {k:(v['median_step_ms_max_over_ranks'], v['augment_call_host_ms_median']) for k,v in d['cfg5'].items()})
+        print('  cfg5', {k:(v['step_ms_max_over_ranks'], v['augment_call_host_ms_median']) for k,v in d['cfg5'].items()})
     except Exception as e: print(n,'failed',e)
 PY
 tail -3 gpurun_out/r2_final_bench_8gpu.err gpurun_out/r2_final_sweep.err
