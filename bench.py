@@ -323,11 +323,11 @@ def measured_peak():
 # ----------------------------------------------------------------------------------------------
 # reference arm
 # ----------------------------------------------------------------------------------------------
-def _reference_worker(conn, method, sample, channels, length, seed, steps, warmup):
+def _reference_worker(conn, method, sample, channels, length, seed, steps, warmup, threads):
     """One process of the reference arm: the UNMODIFIED reference ``augment`` (oracle/_ref, sourceless) on this
-    process's own batch, CPU tensors, one torch thread; reports the seconds its ``steps`` timed steps took."""
+    process's own batch, CPU tensors, ``threads`` torch threads; reports the seconds its ``steps`` timed steps took."""
     import torch
-    torch.set_num_threads(1)
+    torch.set_num_threads(threads)
     from oracle.ref_import import load_reference
     ref1, _ = load_reference(compiled=True)
     data, frames, labels = make_batch(seed, sample, channels, length)
@@ -347,16 +347,18 @@ def _reference_worker(conn, method, sample, channels, length, seed, steps, warmu
     conn.close()
 
 
-def time_reference(method, sample, channels, length, steps, warmup, workers):
-    """Cycles/s of the unmodified reference on this box: ``workers`` processes (one per host core), each running
-    whole steps of ``sample`` cycles on its own batch — the batches are independent, exactly as this repo's
-    ranks shard them.  Returns (cycles/s, seconds of the slowest process)."""
+def time_reference(method, sample, channels, length, steps, warmup, workers, threads=1):
+    """Cycles/s of the unmodified reference on this box: ``workers`` processes with ``threads`` torch threads each,
+    every process running whole steps of ``sample`` cycles on its own batch.  ``workers = 1, threads = all cores`` is
+    the reference as it is (one Python process; SURVEY section 8d's CPU timing); ``workers = cores, threads = 1`` shards
+    independent batches over the cores the way this repo's ranks shard them over GPUs (a stronger baseline than the
+    reference itself offers).  Returns (cycles/s, seconds of the slowest process)."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     procs, pipes = [], []
     for w in range(workers):
         parent, child = ctx.Pipe()
-        p = ctx.Process(target=_reference_worker, args=(child, method, sample, channels, length, 1000 + w, steps, warmup))
+        p = ctx.Process(target=_reference_worker, args=(child, method, sample, channels, length, 1000 + w, steps, warmup, threads))
         p.start()
         procs.append(p)
         pipes.append(parent)
@@ -381,13 +383,20 @@ def run_reference(args):
         return
     workers = os.cpu_count() or 1
     kind = reference_kind()
+    extra = {}
     if kind == "reference":
         sample = max(8, min(args.batch, args.reference_sample))
-        value, elapsed = time_reference(args.method, sample, args.channels, args.length, args.steps, args.warmup, workers)
-        sample_txt = (f"{workers} processes x {args.steps} steps x {sample} cycles x {args.channels} ch x {args.length} samples: the "
-                      f"unmodified reference augment() (oracle/_ref, byte-compiled from the reference tree), one process per host "
-                      f"core, each on its own batches (the full step is {args.batch} cycles; the reference's per-cycle loop is flat in B)")
+        value, elapsed = time_reference(args.method, sample, args.channels, args.length, args.steps, args.warmup, 1, workers)
+        sample_txt = (f"{args.steps} steps x {sample} cycles x {args.channels} ch x {args.length} samples: the unmodified reference "
+                      f"augment() (oracle/_ref, byte-compiled from the reference tree) as it is — one Python process, CPU tensors, "
+                      f"torch.set_num_threads({workers}) (SURVEY 8d) — on a bounded sample of the step (the full step is {args.batch} "
+                      f"cycles; the reference's per-cycle loop is flat in B)")
         ms_per_step = 1e3 * elapsed / args.steps
+        # beside it: independent batches sharded over the cores, one single-threaded reference process per core
+        v_all, _ = time_reference(args.method, sample, args.channels, args.length, max(1, min(args.steps, 3)), 1, workers, 1)
+        extra = {"one_process_per_core": {"value": v_all, "unit": UNIT, "processes": workers,
+                                          "what": "the same unmodified augment(), independent batches sharded over the host cores "
+                                                  "(one single-threaded process per core): a baseline the reference does not offer itself"}}
     else:
         sample = min(args.batch, 1024)
         data, frames, labels = make_batch(7, sample, args.channels, args.length)
@@ -415,7 +424,7 @@ def run_reference(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 mix, f64 spline",
         "data": "synthetic", "config": {"workload": WORKLOAD, "method": args.method, "sample": sample_txt},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample_txt},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample_txt, **extra},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -833,12 +842,15 @@ def run_b200(args):
         workers = os.cpu_count() or 1
         if reference_kind() == "reference":
             sample_b = max(8, min(B, args.reference_sample))
-            steps_ref = 2
             t0 = time.perf_counter()
-            v, _ = time_reference(args.method, sample_b, C, L, steps_ref, 1, workers)
+            v, _ = time_reference(args.method, sample_b, C, L, 6, 1, 1, workers)
+            v_all, _ = time_reference(args.method, sample_b, C, L, 2, 1, workers, 1)
             cpu = {"value": v, "unit": UNIT, "cores": workers, "kind": "reference",
-                   "sample": f"{workers} processes x {steps_ref} steps x {sample_b} cycles x {C} ch x {L}: the unmodified reference "
-                             f"augment() (oracle/_ref), one process per host core; {time.perf_counter() - t0:.1f} s in all"}
+                   "sample": f"6 steps x {sample_b} cycles x {C} ch x {L}: the unmodified reference augment() (oracle/_ref) as it is, one "
+                             f"Python process with torch.set_num_threads({workers}); {time.perf_counter() - t0:.1f} s incl. the leg below",
+                   "one_process_per_core": {"value": v_all, "unit": UNIT, "processes": workers,
+                                            "what": "independent batches sharded over the host cores, one single-threaded reference "
+                                                    "process per core (2 steps each)"}}
         else:
             sample_b = 1024
             v, done, elapsed, _ = time_cpu_baseline(args.method, sample_b, C, L, args.cpu_seconds, workers)
