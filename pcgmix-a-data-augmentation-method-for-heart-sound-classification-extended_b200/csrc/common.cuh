@@ -95,7 +95,8 @@ cudaError_t launch_mix(const MixArgs& base, bool magwarp, bool box, cudaStream_t
 
 // mix_resident.cu — cut + zero-pad + mix(+warp) in one pass over recordings that stay on the device
 cudaError_t launch_mix_resident(const MixArgs& base, bool magwarp, cudaStream_t stream);
-// slot -> {f0..f4, first sample (lo, hi), samples available} records for the pipelined kernel's RESIDENT variant
+// slot -> {f0..f4, first sample in the recording, the recording's first row, samples available} records for the
+// pipelined kernel's RESIDENT variant
 cudaError_t launch_resolve_resident(const MixArgs& a, int32_t* records, cudaStream_t stream);
 
 // mix_pipeline.cu — persistent TMA-pipelined kernel (rows of >= 1024 floats, P % 4 == 0, aligned)

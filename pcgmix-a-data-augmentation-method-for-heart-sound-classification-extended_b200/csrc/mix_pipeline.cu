@@ -32,17 +32,23 @@
 // 16-byte-aligned tensors, P >= 1024.
 //
 // RESIDENT variant (pcgmix_mix1d_resident): the cycle's own samples are not a row of a padded
-// (B, C, L) tensor but lie somewhere inside a recording (mix_resident.cu explains the layout).  A
-// small kernel first resolves every batch slot into an 8-int record {f0..f4, first sample (64 bit),
-// samples available}; the producer reads records instead of `frames`, loads the 16-byte-aligned
-// superset of the slice's samples into a third buffer (obuf) and the partner windows from the
-// partner's recording; consumers take their samples from obuf at the slice's misalignment (two
-// aligned 128-bit shared loads and a select), zero-fill the padding and write the result to xbuf,
-// which leaves through the same bulk store.  Slices that cannot be staged (a superset would run past
-// the end of the tensor, a window reaches into the partner's padding, the windows exceed pbuf) are
-// processed sample by sample from global memory — same result.
+// (B, C, L) tensor but lie somewhere inside a recording (mix_resident.cu explains the layout), at
+// an element offset that is in general NOT a multiple of four.  A small kernel first resolves every
+// batch slot into an 8-int record {f0..f4, first sample inside the recording, first row of the
+// recording, samples available}; the producer reads records instead of `frames`.  Neither kind of
+// TMA copy can move such a cycle to column 0 of xbuf (bulk copies and tensor tiles both need a
+// 16-byte-aligned global start: benchmarks/tma_probe.cu), so the cycle's own samples travel as 4-byte
+// cp.async copies issued by the producer warp — 128 contiguous bytes per warp instruction, no
+// register or scoreboard held while they fly — whose completion arrives on the stage's `full`
+// barrier (cp.async.mbarrier.arrive.noinc) next to the partner windows' transaction bytes.
+// Consumers zero the columns behind the cycle's last sample (padding), blend and warp in place like the padded variant; the slice leaves through the same
+// bulk store.  Partner windows are bulk copies of 16-byte-aligned supersets out of the partner's
+// recording; a slice whose windows cannot be staged (a window reaches into the partner's padding, a
+// superset would run past the end of the tensor, the windows exceed pbuf) reads its partner samples
+// one by one from global memory — same result.
 
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -69,20 +75,28 @@ __device__ __forceinline__ unsigned long long global_ns() {
 #endif
 
 constexpr int kMaxStages = 8;
+constexpr int kResidentStages = 6;      // RESIDENT default: two CTAs per SM (registers), six stages each fill the shared memory
 constexpr int kHeaderBytes = 1024;
 constexpr int kProducerWarps = 2;       // producer warps take alternate items (one warp's instruction stream per
                                         // item, ~600 dependent instructions with the spline set-up, was the bound)
-constexpr int kHelperThreads = 32 + 32 * kProducerWarps;   // the LAST warps of the CTA: store warp, then producers
+constexpr int kResidentProducerWarps = 3;   // RESIDENT: a producer also issues the cycle's own samples as 4-byte copies
+// the LAST warps of the CTA are the store warp, then the producers
                                        // (the SM's issue arbiter favours high warp ids; a producer in warp 0
                                        // is starved by consumer warps polling their barriers)
 // PCGmix+ on padded batches replaces the second producer warp by the coefficient warp (see the kernel): its
 // producers no longer touch the knots, and a 14th warp would cost every thread 8 registers at three CTAs per SM.
-// The RESIDENT variant (two CTAs per SM, heavier producers: own and partner supersets) keeps both producers.
+// The RESIDENT variant (two CTAs per SM; a producer also issues the cycle's own samples as 4-byte copies) has three.
 __host__ __device__ constexpr int producer_warps(int warp_variant, bool resident) {
-    return (warp_variant != 0 && !resident) ? 1 : kProducerWarps;
+    return resident ? kResidentProducerWarps : (warp_variant != 0 ? 1 : kProducerWarps);
+}
+// Coefficient warps (PCGmix+ only) take alternate items like the producers.  One suffices at three CTAs per SM (37
+// items per CTA per launch at the benchmark size); the RESIDENT variant's two CTAs per SM serve 55 items each, and one
+// warp's dependent chain per item (~1.2 us among the polling consumer warps) was its bound.
+__host__ __device__ constexpr int coefficient_warps(int warp_variant, bool resident) {
+    return warp_variant == 0 ? 0 : (resident ? 2 : 1);
 }
 __host__ __device__ constexpr int helper_threads(int warp_variant, bool resident) {
-    return 32 + 32 * producer_warps(warp_variant, resident) + (warp_variant != 0 ? 32 : 0);
+    return 32 + 32 * producer_warps(warp_variant, resident) + 32 * coefficient_warps(warp_variant, resident);
 }
 
 struct StageMeta {
@@ -93,9 +107,8 @@ struct StageMeta {
     int nvec;                  // 128-bit vectors in this slice
     int t_beg;                 // first column of the slice
     // RESIDENT only
-    const float* own_g;        // the slice's own samples in global memory (column 0 of the slice)
     int own_n;                 // columns of the slice that hold samples (the rest is padding)
-    int own_shift;             // staged: floats between obuf[0] and column 0; -1: slice not staged (use own_g / pbase)
+    int par_global;            // 1: partner windows not staged — pbase points into `signal`, guard reads with par_n
     int par_n;                 // not staged: partner columns (slice-local, before the window shift) that hold samples
     int positive;              // 1: the row's warp factor is certainly > 0 and finite at every sample
     int exact;                 // float32 variant: 1 = coef holds float64 coefficients in powers of dt (the row's factor
@@ -132,6 +145,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+// global -> shared asynchronous copy of one float (any 4-byte-aligned pair of addresses)
+__device__ __forceinline__ void async_copy_f32(uint32_t dst_smem, const float* src_gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src_gmem) : "memory");
+}
+// one (pre-counted) arrival on `bar` once every cp.async this thread has issued so far has landed
+__device__ __forceinline__ void async_copies_arrive(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 // shared -> global bulk copy; one bulk group per call
 __device__ __forceinline__ void bulk_store(void* dst_gmem, const void* src_smem, uint32_t bytes) {
@@ -203,7 +224,8 @@ struct PipeArgs {
     int debug;                 // profiling only: 1 = skip stores, 2 = skip arithmetic, 4 = skip partner copies
 };
 
-// WARP: 0 = PCGmix (no magnitude warp); 1 = PCGmix+ with the warp factor evaluated in float64 and the product
+// WARP: 3 and 4 are 1 and 2 for rows with more than 32 coefficients (knot > 7), a separate instance because of the
+// coefficient warp (see there).  0 = PCGmix (no magnitude warp); 1 = PCGmix+ with the warp factor evaluated in float64 and the product
 // fp64(sample) * w rounded once to fp32, like the reference's float64 product stored into a float32 array
 // (> 99.9 % of samples bit-equal to it); 2 = PCGmix+ with the factor evaluated in float32 (normalised Horner,
 // coefficients rounded from float64) and an fp32 product: within 1e-5 relative of the reference (typically
@@ -217,7 +239,8 @@ template <int NCT, int WARP, int VPT, bool RESIDENT>
 __global__ void __launch_bounds__(NCT + helper_threads(WARP, RESIDENT), RESIDENT ? 2 : (NCT <= 192 ? 4 : NCT <= 320 ? 3 : 2))
 mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ PipeArgs pa) {
     constexpr bool MAGWARP = WARP != 0;
-    constexpr bool F32 = WARP == 2;
+    constexpr bool F32 = WARP == 2 || WARP == 4;
+    constexpr bool WIDE = WARP >= 3;          // knot > 7: more than 32 coefficients per row (lane l owns l, l+32, l+64, l+96)
     constexpr int kThreads = NCT + helper_threads(WARP, RESIDENT);
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t* full = reinterpret_cast<uint64_t*>(smem);                  // loads of the stage have landed
@@ -252,7 +275,9 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
 #endif
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], MAGWARP ? 2 : 1);      // producer (+ the row's coefficients from the coefficient warp)
+            // producer (+ the row's coefficients from the coefficient warp) (+ RESIDENT: the producer warp's 32 lanes,
+            // each when its share of the cycle's own samples has landed)
+            mbar_init(&full[s], (MAGWARP ? 2 : 1) + (RESIDENT ? 32 : 0));
             mbar_init(&computed[s], NCT);
             mbar_init(&empty[s], 1);
         }
@@ -273,8 +298,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     __syncthreads();
 
     auto stage_x = [&](int s) { return reinterpret_cast<float*>(stages + static_cast<size_t>(s) * pa.stage_bytes); };
-    auto stage_o = [&](int s) { return stage_x(s) + pa.slice_cap; };                      // RESIDENT: slice_cap + 8 floats
-    auto stage_p = [&](int s) { return stage_x(s) + pa.slice_cap + (RESIDENT ? pa.slice_cap + 8 : 0); };
+    auto stage_p = [&](int s) { return stage_x(s) + pa.slice_cap; };
     auto stage_meta = [&](int s) { return reinterpret_cast<StageMeta*>(stage_p(s) + pa.pbuf_cap); };
     // items of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
     const int n_it = (pa.n_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -304,7 +328,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
     auto row_of = [&](Cursor c) { return pa.slices_per_row == 1 ? c.rest : c.rest / pa.slices_per_row; };
 
     if (MAGWARP && threadIdx.x >= NCT + 32 + 32 * producer_warps(WARP, RESIDENT)) {
-        // =================================== coefficient warp ====================================
+        // =================================== coefficient warps ===================================
         // Turns every item's K+2 knots into the 4(K+1) cubic coefficients its consumers need (coefficient i =
         // sum_j M[i][j] * knot_j, matrix in shared memory, knots broadcast by shuffle) and writes them into the
         // item's stage, then arrives on the stage's `full` barrier next to the producer.  Nothing else depends
@@ -314,9 +338,14 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         const int lane = threadIdx.x & 31;
         const int n_knots = a.K + 2;
         const int n_coef = (a.K + 1) * 4;
-        const bool wide = n_coef > 32;
-        auto knot_of = [&](Cursor c) {                      // lane j: knot j of the item's (cycle, row)
-            const int b = cycle_of_slot(a, c.slot);
+        constexpr int NC = coefficient_warps(WARP, RESIDENT);
+        const int cw = (threadIdx.x - (NCT + 32 + 32 * producer_warps(WARP, RESIDENT))) >> 5;   // this warp: items cw, cw + NC, ...
+        // order[slot] -> knots[cycle] is a chain of two dependent loads: the cycle id is fetched two items ahead and
+        // the knots one item ahead, so in steady state this warp never waits for memory.  (An id outside [0, B) is
+        // replaced by the slot like everywhere else; the producer warp is the one that raises BAD_PARTNER for it.)
+        auto raw_cycle = [&](Cursor c) { return a.order == nullptr ? c.slot : __ldg(a.order + c.slot); };
+        auto knot_of = [&](int raw, Cursor c) {             // lane j: knot j of the item's (cycle, row)
+            const int b = static_cast<unsigned>(raw) < static_cast<unsigned>(a.B) ? raw : c.slot;
             double y = 0.0;
             if (lane < n_knots && !PCGMIX_SKIP(16)) y = __ldg(a.knots + (static_cast<size_t>(b) * n_knots + lane) * a.R + row_of(c));
             return y;
@@ -326,24 +355,24 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         // like unsigned integers; NaN orders above every bound).
         unsigned safe_dev_bits = 0u;
         if constexpr (RESIDENT) safe_dev_bits = __float_as_uint(__double2float_rd(fmax(__ldg(a.knot_pos + a.K + 2), 0.0)));
-        Cursor c0{static_cast<int>(blockIdx.x % a.B), static_cast<int>(blockIdx.x / a.B)};
-        Cursor c1 = advance1(c0);
-        double y_next = n_it > 0 ? knot_of(c0) : 0.0;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int it = 0; it < n_it; ++it) {
-            const double y_cur = y_next;
-            if (it + 1 < n_it) y_next = knot_of(c1);        // one item ahead: its latency hides behind this item's arithmetic
-            c1 = advance1(c1);
-            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;      // lane l owns coefficients l, l+32, l+64, l+96 (the last three: knot > 7)
-            const double* mrow = s_mat + lane * n_knots;
+        // float32 variant: coefficient i of a piece is scaled by h^(3 - (i & 3))
+        const int power = 3 - (lane & 3);
+        const double scale = power == 3 ? h_piece * h_piece * h_piece : power == 2 ? h_piece * h_piece : power == 1 ? h_piece : 1.0;
+        // One item's coefficients -> its stage.  The narrow and the WIDE form are different kernel instances: this warp's
+        // dependent chain per item is on the critical path (it shares its scheduler with polling consumer warps), and
+        // with both forms in one kernel the narrow one ran 10 % slower (profiles/README.md).
+        auto coefficients_of_item = [&](const double y_cur, const int stage, const uint32_t phase) {
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+            const double* mrow = s_mat + ((WIDE || lane < n_coef) ? lane : 0) * n_knots;   // (idle lanes redo row 0; never stored)
             for (int j = 0; j < (PCGMIX_SKIP(8) ? 0 : n_knots); ++j) {
                 const double yj = __shfl_sync(kFullMask, y_cur, j);
-                if (lane < n_coef) acc0 = fma(mrow[j], yj, acc0);
-                if (wide) {
+                if constexpr (WIDE) {
+                    if (lane < n_coef) acc0 = fma(mrow[j], yj, acc0);
                     if (lane + 32 < n_coef) acc1 = fma(mrow[32 * n_knots + j], yj, acc1);
                     if (lane + 64 < n_coef) acc2 = fma(mrow[64 * n_knots + j], yj, acc2);
                     if (lane + 96 < n_coef) acc3 = fma(mrow[96 * n_knots + j], yj, acc3);
+                } else {
+                    acc0 = fma(mrow[j], yj, acc0);
                 }
             }
             // float32 variant: coefficients of u = dt/h (lane i: power 3 - (i & 3) of h), and is the factor certainly
@@ -352,27 +381,24 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             int exact = 0;
             float c32[4] = {0.0f, 0.0f, 0.0f, 0.0f};
             if constexpr (F32) {
-                const int power = 3 - (lane & 3);
-                const double scale = power == 3 ? h_piece * h_piece * h_piece : power == 2 ? h_piece * h_piece : power == 1 ? h_piece : 1.0;
                 c32[0] = static_cast<float>(acc0 * scale);
-                c32[1] = static_cast<float>(acc1 * scale);
-                c32[2] = static_cast<float>(acc2 * scale);
-                c32[3] = static_cast<float>(acc3 * scale);
-                float lowest = INFINITY;
+                if constexpr (WIDE) {
+                    c32[1] = static_cast<float>(acc1 * scale);
+                    c32[2] = static_cast<float>(acc2 * scale);
+                    c32[3] = static_cast<float>(acc3 * scale);
+                }
+                bool low = false;                               // a Bernstein coefficient below 1/16 (or NaN) on this lane
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    if (g > 0 && !wide) break;
+                for (int g = 0; g < (WIDE ? 4 : 1); ++g) {
                     const int base = lane & ~3;
                     const float ca = __shfl_sync(kFullMask, c32[g], base), cb = __shfl_sync(kFullMask, c32[g], base + 1);
                     const float cc = __shfl_sync(kFullMask, c32[g], base + 2), cd = __shfl_sync(kFullMask, c32[g], base + 3);
                     const int k = lane & 3;
                     const float bern = k == 0 ? cd : k == 1 ? cd + cc * (1.0f / 3.0f)
                                      : k == 2 ? cd + cc * (2.0f / 3.0f) + cb * (1.0f / 3.0f) : ca + cb + cc + cd;
-                    if (lane + 32 * g < n_coef) lowest = fminf(lowest, bern == bern ? bern : -INFINITY);
+                    if (lane + 32 * g < n_coef) low = low || !(bern >= 0.0625f);
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) lowest = fminf(lowest, __shfl_xor_sync(kFullMask, lowest, o));
-                exact = lowest >= 0.0625f ? 0 : 1;
+                exact = __any_sync(kFullMask, low) ? 1 : 0;
                 if (PCGMIX_SKIP(64)) exact = 0;                 // (profiling: never take the float64 path)
             }
             // RESIDENT: the curve reproduces constants and is linear in the knots, |w(t) - 1| <= Lambda * max_j |y_j - 1|.
@@ -381,21 +407,25 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             int row_positive = 0;
             if constexpr (RESIDENT) {
                 const float dev = lane < n_knots ? fabsf(static_cast<float>(y_cur) - 1.0f) : 0.0f;
-                row_positive = __reduce_max_sync(kFullMask, __float_as_uint(dev)) < safe_dev_bits ? 1 : 0;
+                row_positive = __all_sync(kFullMask, __float_as_uint(dev) < safe_dev_bits) ? 1 : 0;
             }
             mbar_wait(&empty[stage], phase ^ 1);            // the stage's previous slice has left shared memory
             StageMeta* meta = stage_meta(stage);
             if (F32 && !exact) {
                 float* out32 = reinterpret_cast<float*>(meta->coef);
                 if (lane < n_coef) out32[lane] = c32[0];
-                if (lane + 32 < n_coef) out32[lane + 32] = c32[1];
-                if (lane + 64 < n_coef) out32[lane + 64] = c32[2];
-                if (lane + 96 < n_coef) out32[lane + 96] = c32[3];
+                if constexpr (WIDE) {
+                    if (lane + 32 < n_coef) out32[lane + 32] = c32[1];
+                    if (lane + 64 < n_coef) out32[lane + 64] = c32[2];
+                    if (lane + 96 < n_coef) out32[lane + 96] = c32[3];
+                }
             } else {
                 if (lane < n_coef) meta->coef[lane] = acc0;
-                if (lane + 32 < n_coef) meta->coef[lane + 32] = acc1;
-                if (lane + 64 < n_coef) meta->coef[lane + 64] = acc2;
-                if (lane + 96 < n_coef) meta->coef[lane + 96] = acc3;
+                if constexpr (WIDE) {
+                    if (lane + 32 < n_coef) meta->coef[lane + 32] = acc1;
+                    if (lane + 64 < n_coef) meta->coef[lane + 64] = acc2;
+                    if (lane + 96 < n_coef) meta->coef[lane + 96] = acc3;
+                }
             }
             if (lane == 0) {
                 meta->exact = exact;
@@ -403,8 +433,30 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[stage]);
-            if (++stage == S) {
-                stage = 0;
+        };
+        auto advance_c = [&](Cursor c) {                    // to this warp's next item
+#pragma unroll
+            for (int k = 0; k < NC; ++k) c = advance1(c);
+            return c;
+        };
+        Cursor c0{static_cast<int>(blockIdx.x % a.B), static_cast<int>(blockIdx.x / a.B)};
+        for (int k = 0; k < cw; ++k) c0 = advance1(c0);
+        Cursor c1 = advance_c(c0);
+        int raw1 = n_it > cw + NC ? raw_cycle(c1) : 0;
+        double y_next = n_it > cw ? knot_of(raw_cycle(c0), c0) : 0.0;
+        int stage = cw % S;
+        uint32_t phase = (cw / S) & 1;
+        for (int it = cw; it < n_it; it += NC) {
+            const double y_cur = y_next;
+            const Cursor c2 = advance_c(c1);
+            const int raw2 = it + 2 * NC < n_it ? raw_cycle(c2) : 0;
+            if (it + NC < n_it) y_next = knot_of(raw1, c1); // both latencies hide behind this item's arithmetic
+            raw1 = raw2;
+            c1 = c2;
+            coefficients_of_item(y_cur, stage, phase);
+            stage += NC;                                   // NC <= S is guaranteed by the launcher
+            if (stage >= S) {
+                stage -= S;
                 phase ^= 1;
             }
         }
@@ -436,7 +488,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                     f2 = f1 + __ldg(w + 2);
                 }
             } else if (lane < (RESIDENT ? 8 : 5)) {
-                // RESIDENT: lanes 5..7 carry {first sample lo, hi, samples available} of the slot's record
+                // RESIDENT: lanes 5..7 carry {first sample in the recording, the recording's first row, samples available}
                 f1 = __ldg(a.frames + static_cast<size_t>(b) * a.frame_stride + lane);
                 f2 = __ldg(a.frames + static_cast<size_t>(p) * a.frame_stride + lane);
             }
@@ -511,11 +563,8 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             int own_n = 0, par_n = 0, par_mis = 0;
             bool stageable = true;
             if constexpr (RESIDENT) {
-                const long long chan = static_cast<long long>(row) * a.T_sig;
-                own_first = ((static_cast<long long>(__shfl_sync(kFullMask, f1_cur, 6)) << 32) |
-                             static_cast<unsigned>(__shfl_sync(kFullMask, f1_cur, 5))) + chan;
-                par_first = ((static_cast<long long>(__shfl_sync(kFullMask, f2_cur, 6)) << 32) |
-                             static_cast<unsigned>(__shfl_sync(kFullMask, f2_cur, 5))) + chan;
+                own_first = static_cast<long long>(__shfl_sync(kFullMask, f1_cur, 6) + row) * a.T_sig + __shfl_sync(kFullMask, f1_cur, 5);
+                par_first = static_cast<long long>(__shfl_sync(kFullMask, f2_cur, 6) + row) * a.T_sig + __shfl_sync(kFullMask, f2_cur, 5);
                 own_n = __shfl_sync(kFullMask, f1_cur, 7);
                 par_n = __shfl_sync(kFullMask, f2_cur, 7);
                 par_mis = static_cast<int>((par_first + w_beg + d) & 3);      // misalignment of the window's first partner sample
@@ -536,13 +585,8 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
             const int off = incl - cnt;
             int total = __shfl_sync(kFullMask, incl, 3);
-            // the slice's own samples (RESIDENT): aligned superset [own_lo, own_lo + own_cnt) of the tensor
+            // the slice's own samples (RESIDENT): own_local of them, the first one goes to column 0 of xbuf
             const int own_local = RESIDENT ? min(max(own_n - t_beg, 0), t_end - t_beg) : 0;
-            const int own_shift = RESIDENT ? static_cast<int>((own_first + t_beg) & 3) : 0;
-            const int own_cnt = own_local > 0 ? ((own_shift + own_local + 3) & ~3) : 0;
-            if constexpr (RESIDENT) {
-                if (own_first + t_beg - own_shift + own_cnt > a.n_sig) stageable = false;
-            }
             const bool staged = total <= pa.pbuf_cap && !PCGMIX_SKIP(4) && stageable;   // else: consumers read from global memory
             if (!staged) {
                 have = false;
@@ -566,9 +610,8 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             if (lane == 0) {
                 meta->pbase = staged ? pbuf : (src_base + prow + t_beg);
                 if constexpr (RESIDENT) {
-                    meta->own_g = a.signal + own_first + t_beg;
                     meta->own_n = own_local;
-                    meta->own_shift = staged ? own_shift : -1;
+                    meta->par_global = staged ? 0 : 1;
                     meta->par_n = par_n - t_beg;
                 }
                 meta->out_offset = row_off + t_beg;
@@ -579,11 +622,19 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
             __syncwarp();
             if constexpr (RESIDENT) {
-                const int own_load = staged ? own_cnt : 0;
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(own_load + total) * 4u);
-                    if (own_load > 0)
-                        bulk_load(stage_o(stage), a.signal + (own_first + t_beg - own_shift), static_cast<uint32_t>(own_load) * 4u, &full[stage]);
+                if (lane == 0) mbar_arrive_expect_tx(&full[stage], static_cast<uint32_t>(total) * 4u);
+                {
+                    const float* own_g = a.signal + (own_first + t_beg) + lane;
+                    uint32_t dst = smem_addr(xbuf) + 4u * lane;
+                    int i = lane;
+                    for (; i + 96 < own_local; i += 128, own_g += 128, dst += 512u) {      // four copies per round of address arithmetic
+                        async_copy_f32(dst, own_g);
+                        async_copy_f32(dst + 128u, own_g + 32);
+                        async_copy_f32(dst + 256u, own_g + 64);
+                        async_copy_f32(dst + 384u, own_g + 96);
+                    }
+                    for (; i < own_local; i += 32, own_g += 32, dst += 128u) async_copy_f32(dst, own_g);
+                    async_copies_arrive(&full[stage]);
                 }
                 if (have) bulk_load(pbuf + off, a.signal + prow + src_lo, static_cast<uint32_t>(cnt) * 4u, &full[stage]);
             } else {
@@ -669,10 +720,8 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             const bool exact = F32 && meta->exact != 0;
             const double* coef = meta->coef;
             const float* coef32 = reinterpret_cast<const float*>(meta->coef);
-            const float* obuf = stage_o(stage);
-            const float* own_g = RESIDENT ? meta->own_g : nullptr;
             const int own_n = RESIDENT ? meta->own_n : 0;
-            const int own_shift = RESIDENT ? meta->own_shift : 0;
+            const bool par_global = RESIDENT && meta->par_global != 0;
             const int par_n = RESIDENT ? meta->par_n : 0;
             const bool positive = RESIDENT && MAGWARP && meta->positive != 0;
 #pragma unroll
@@ -682,37 +731,15 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                     const int col = v * 4;                                   // local column
                     float r[4];
                     if constexpr (RESIDENT) {
-                        if (__builtin_expect(own_shift < 0, 0)) {            // slice not staged: sample by sample from global memory
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int t = col + e;
-                                r[e] = t < own_n ? __ldg(own_g + t) : 0.0f;
-                                const int se = (t >= lo1) + (t >= lo2) + (t >= lo3);
-                                const int4 we = meta->win[se];
-                                if (static_cast<unsigned>(t - we.x) < static_cast<unsigned>(we.y)) {
-                                    const float o = t + we.z < par_n ? __ldg(pbase + t + we.z) : 0.0f;
-                                    r[e] = __fadd_rn(__fmul_rn(r[e], a.lam), __fmul_rn(o, a.one_minus_lam));
-                                }
-                            }
-                        } else {
-                            r[0] = r[1] = r[2] = r[3] = 0.0f;
-                            if (col < own_n) {
-                                const float4 lo = *reinterpret_cast<const float4*>(obuf + col);
-                                const float4 hi = *reinterpret_cast<const float4*>(obuf + col + 4);
-                                if (own_shift == 0) {                        // uniform over the item
-                                    r[0] = lo.x; r[1] = lo.y; r[2] = lo.z; r[3] = lo.w;
-                                } else if (own_shift == 1) {
-                                    r[0] = lo.y; r[1] = lo.z; r[2] = lo.w; r[3] = hi.x;
-                                } else if (own_shift == 2) {
-                                    r[0] = lo.z; r[1] = lo.w; r[2] = hi.x; r[3] = hi.y;
-                                } else {
-                                    r[0] = lo.w; r[1] = hi.x; r[2] = hi.y; r[3] = hi.z;
-                                }
-                                if (col + 4 > own_n) {                       // the vector holding the cycle's last sample
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) r[e] = col + e < own_n ? r[e] : 0.0f;
-                                }
-                            }
+                        // the cycle's samples start at column 0 (the tensor copy put them there); columns from own_n on
+                        // are padding, whatever the last box or the stage's previous slice left there
+                        r[0] = r[1] = r[2] = r[3] = 0.0f;
+                        if (col < own_n) {
+                            const float4 mine = *reinterpret_cast<const float4*>(xbuf + col);
+                            r[0] = mine.x;
+                            r[1] = col + 1 < own_n ? mine.y : 0.0f;
+                            r[2] = col + 2 < own_n ? mine.z : 0.0f;
+                            r[3] = col + 3 < own_n ? mine.w : 0.0f;
                         }
                     } else {
                         const float4 mine = *reinterpret_cast<const float4*>(xbuf + col);
@@ -722,9 +749,20 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                     const int4 w = meta->win[s];
                     const int ahead = col - w.x;
                     // padding that no window touches: +0.0f, and +0.0f times a positive finite factor is +0.0f
-                    bool padding = RESIDENT && MAGWARP && positive && own_shift >= 0 && col >= own_n;
-                    if (RESIDENT && own_shift < 0) {
-                        // blended above
+                    bool padding = RESIDENT && MAGWARP && positive && col >= own_n;
+                    if (RESIDENT && __builtin_expect(par_global, 0)) {
+                        // partner windows not staged: sample by sample out of the partner's recording, zeros behind its end
+                        padding = false;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int t = col + e;
+                            const int se = (t >= lo1) + (t >= lo2) + (t >= lo3);
+                            const int4 we = meta->win[se];
+                            if (static_cast<unsigned>(t - we.x) < static_cast<unsigned>(we.y)) {
+                                const float o = t + we.z < par_n ? __ldg(pbase + t + we.z) : 0.0f;
+                                r[e] = __fadd_rn(__fmul_rn(r[e], a.lam), __fmul_rn(o, a.one_minus_lam));
+                            }
+                        }
                     } else if (__builtin_expect(ahead >= 0 && col + 3 < w.w, 1)) {
                         const int m = w.y - ahead;                           // leading samples that blend
                         if (m > 0) {
@@ -825,7 +863,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 if (__builtin_expect(exact, 0)) exact_warp_pass(a, s_kpos, s_kint, coef, xbuf, nvec, t_beg, ct, NCT, VPT);
             }
             fence_async_proxy();                           // my shared-memory writes -> visible to the TMA engine
-            mbar_arrive(&computed[stage]);
+            mbar_arrive(&computed[stage]);                 // (one arrival per warp instead of per thread: measured, no gain)
             if (++stage == S) {
                 stage = 0;
                 phase ^= 1;
@@ -927,7 +965,9 @@ cudaError_t launch_instance(const MixArgs& a, PipeArgs pa, size_t smem, GridPlan
 
 template <int NCT, int VPT, bool RESIDENT>
 cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, size_t smem, int warp, const GridPlan& plan, cudaStream_t stream) {
-    return warp == 2 ? launch_instance<NCT, 2, VPT, RESIDENT>(a, pa, smem, plan, stream)
+    return warp == 4 ? launch_instance<NCT, 4, VPT, RESIDENT>(a, pa, smem, plan, stream)
+         : warp == 3 ? launch_instance<NCT, 3, VPT, RESIDENT>(a, pa, smem, plan, stream)
+         : warp == 2 ? launch_instance<NCT, 2, VPT, RESIDENT>(a, pa, smem, plan, stream)
          : warp == 1 ? launch_instance<NCT, 1, VPT, RESIDENT>(a, pa, smem, plan, stream)
                      : launch_instance<NCT, 0, VPT, RESIDENT>(a, pa, smem, plan, stream);
 }
@@ -962,7 +1002,8 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     DeviceFacts facts{};
     if (const cudaError_t e = device_facts(&device, &facts)) return e;
     const int g_sm_count = facts.sm_count;
-    const int warp = magwarp ? (tune.spline_f32 ? 2 : 1) : 0;      // kernel variant, see mix_pipeline_kernel
+    // kernel variant, see mix_pipeline_kernel: +2 when a row has more than 32 coefficients
+    const int warp = magwarp ? (tune.spline_f32 ? 2 : 1) + ((a.K + 1) * 4 > 32 ? 2 : 0) : 0;
     PipeArgs pa{};
     const int max_slice = tune.max_slice > 0 ? (tune.max_slice > 3584 ? 3584 : tune.max_slice) : 3584;   // 448 threads x 2 vectors
     pa.slices_per_row = (a.P + max_slice - 1) / max_slice;
@@ -974,11 +1015,11 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     // falls back to reading the partner from global memory (still exact, just not staged)
     const int pbuf_pct = tune.pbuf_pct > 0 ? tune.pbuf_pct : 62;
     pa.pbuf_cap = ((slice_len * pbuf_pct / 100 + 32) + 31) & ~31;
-    pa.stages = tune.stages > 0 ? (tune.stages > kMaxStages ? kMaxStages : tune.stages) : 4;
-    if (pa.stages < kProducerWarps) pa.stages = kProducerWarps;
+    pa.stages = tune.stages > 0 ? (tune.stages > kMaxStages ? kMaxStages : tune.stages) : (resident ? kResidentStages : 4);
+    if (pa.stages < kResidentProducerWarps) pa.stages = kResidentProducerWarps;
     // only the (K+1)*4 coefficients in use are reserved at the end of the metadata block
     const size_t meta_bytes = sizeof(StageMeta) - sizeof(double) * (kMaxPieces * 4 - (magwarp ? (a.K + 1) * 4 : 0));
-    const size_t stage_bytes = (static_cast<size_t>(pa.slice_cap) * (resident ? 2 : 1) + (resident ? 8 : 0) + pa.pbuf_cap) * sizeof(float) + meta_bytes;
+    const size_t stage_bytes = (static_cast<size_t>(pa.slice_cap) + pa.pbuf_cap) * sizeof(float) + meta_bytes;
     pa.stage_bytes = static_cast<int>((stage_bytes + 127) & ~static_cast<size_t>(127));
     const size_t mat_bytes = magwarp ? static_cast<size_t>(a.K + 1) * 4 * (a.K + 2) * sizeof(double) : 0;
     const long long n_items = static_cast<long long>(a.B) * a.R * pa.slices_per_row;
@@ -1001,9 +1042,10 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     const int by_threads = 2048 / (nct + helper_threads(warp, resident));
     per_sm = per_sm < by_threads ? per_sm : by_threads;
     if (tune.ctas_per_sm > 0 && tune.ctas_per_sm < per_sm) per_sm = tune.ctas_per_sm;
-    if (pa.stages < kProducerWarps) return cudaErrorInvalidConfiguration;
+    if (pa.stages < kResidentProducerWarps) return cudaErrorInvalidConfiguration;
     GridPlan plan{device, g_sm_count, per_sm, overlap_previous, previous_signature, full_grid_signature};
     if (resident) {
+        if (static_cast<long long>(a.n_rec) * a.R > 2147483647LL) return cudaErrorInvalidConfiguration;   // the records hold rows as int32
         // launched with the programmatic attribute: the kernel right before it on the stream is the slot-record
         // kernel, which lets it start early; the producers wait for the records (griddepcontrol.wait)
         plan.overlap_previous = true;

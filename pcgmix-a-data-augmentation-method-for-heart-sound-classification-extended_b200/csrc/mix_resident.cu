@@ -312,8 +312,8 @@ cudaError_t launch_t(const MixArgs& a, dim3 grid, bool magwarp, cudaStream_t str
 }
 
 // One thread per batch slot: the slot's table row resolved into the 8-int record the pipelined
-// kernel reads instead of `frames`: {f0..f4, first sample of channel 0 (64-bit element index, lo/hi),
-// samples available}.  A slot whose table row or recording does not exist gets an empty record (all
+// kernel reads instead of `frames`: {f0..f4, first sample inside the recording, row of the recording's channel 0
+// in `signal` viewed as [n_rec * R][T_sig], samples available}.  A slot whose table row or recording does not exist gets an empty record (all
 // padding, nothing blended) and raises PCGMIX_ERR_BAD_PARTNER.
 __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ MixArgs a, int32_t* __restrict__ records) {
     // the pipelined kernel behind us may start its prologue now; it waits (griddepcontrol.wait) for this
@@ -331,9 +331,8 @@ __global__ void __launch_bounds__(256) resolve_kernel(const __grid_constant__ Mi
         if (ok) {
             const int start = min(max(head.y, 0), a.T_sig);
             const int stop = min(max(head.z, start), a.T_sig);
-            const long long first = static_cast<long long>(head.x) * a.R * a.T_sig + start;
             lo = make_int4(head.w, tail.x, tail.y, tail.z);
-            hi = make_int4(tail.w, static_cast<int>(first & 0xffffffffLL), static_cast<int>(first >> 32), min(stop - start, a.P));
+            hi = make_int4(tail.w, start, head.x * a.R, min(stop - start, a.P));
         }
     }
     reinterpret_cast<int4*>(records)[static_cast<size_t>(b) * 2] = lo;

@@ -74,6 +74,12 @@ class NativeLibraryError(RuntimeError):
 
 
 def library_path() -> str:
+    # PCGMIX_LIB=<path>: a differently built library of the same ABI (kernel experiments: benchmarks/build_variant.py)
+    override = os.environ.get("PCGMIX_LIB")
+    if override:
+        if not os.path.exists(override):
+            raise NativeLibraryError(f"PCGMIX_LIB points to {override}, which does not exist")
+        return override
     # PCGMIX_PROFILING_LIB=1: the build with the skip switches compiled in (profiling scripts only)
     if os.environ.get("PCGMIX_PROFILING_LIB") == "1" and os.path.exists(build_native.PROFILING_LIB_PATH):
         return build_native.PROFILING_LIB_PATH

@@ -16,3 +16,9 @@ for l in sys.stdin:
     if l.startswith('{'):
         d=json.loads(l)
         if 'fused' in d['config']: print(d['config'][:40], round(d['ms_mean'],4), round(d.get('frac_of_measured_peak',0),3))"
+timeout 120 python benchmarks/run_configs.py --only resident --reps 100 --spline float64 2>/dev/null | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l)
+        if 'fused' in d['config']: print('float64', d['config'][:40], round(d['ms_mean'],4), round(d.get('frac_of_measured_peak',0),3))"
