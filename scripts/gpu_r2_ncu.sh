@@ -5,9 +5,11 @@ B="python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-configs --no-var
 $B > gpurun_out/r2n_plain.json 2> gpurun_out/r2n_plain.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench_steps20.csv $B > gpurun_out/r2n_ncu0.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:mix_pipeline -s 10 -c 2 -o gpurun_out/r2_prof_headline -f $B --no-graph > gpurun_out/r2n_ncu1.log 2>&1
+if [ "$1" = "all" ]; then
 R="python benchmarks/run_configs.py --reps 20"
 $R > gpurun_out/r2n_configs.jsonl 2> gpurun_out/r2n_configs.err || exit 1
 ncu --set full --clock-control none --import-source on -k regex:mix_kernel -s 12 -c 1 -o gpurun_out/r2_prof_cfg3_flat -f $R > gpurun_out/r2n_ncu2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:mix_pipeline -s 700 -c 1 -o gpurun_out/r2_prof_resident -f python benchmarks/run_configs.py --only resident --reps 20 > gpurun_out/r2n_ncu3.log 2>&1
-tail -n 2 gpurun_out/r2n_ncu1.log gpurun_out/r2n_ncu2.log gpurun_out/r2n_ncu3.log
+ncu --set full --clock-control none --import-source on -k regex:mix_pipeline --launch-skip 12 -c 1 -o gpurun_out/r2_prof_resident -f python benchmarks/run_configs.py --only resident --reps 10 > gpurun_out/r2n_ncu3.log 2>&1
+fi
+tail -n 2 gpurun_out/r2n_ncu1.log
 ls -la gpurun_out/*.ncu-rep
