@@ -1,16 +1,11 @@
 #!/bin/bash
-# A/B: the shipped library against variants built by benchmarks/build_variant.py (PCGMIX_LIB=...), RESIDENT timings
+# A/B: the shipped library against variants built by benchmarks/build_variant.py (PCGMIX_LIB=...), config 2 timings
 mkdir -p gpurun_out
 V="pcgmix-a-data-augmentation-method-for-heart-sound-classification-extended_b200/csrc/variants"
 for lib in "" $(ls $V/*.so 2>/dev/null); do
   echo "=== ${lib:-shipped}"
-  for extra in "" "--stages 3" "--stages 5"; do
-  PCGMIX_LIB=$lib timeout -s KILL 200 python benchmarks/run_configs.py --only resident --reps 100 $extra 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    try: d=json.loads(l)
-    except Exception: continue
-    if 'fused' in d['config']: print('   $extra', d['config'][:40], 'ms', round(d.get('ms_mean',0),4), 'frac', round(d.get('frac_of_measured_peak',0),4))
-"
+  for prec in float32 float64; do
+  PCGMIX_LIB=$lib timeout 120 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --e2e-steps 3 --no-configs --no-variants --no-cfg5 --spline $prec 2>gpurun_out/kc.err | python -c "
+import sys,json; d=json.loads(sys.stdin.read()); r=d['roofline']; print('  pcgmix+ $prec', 'overlapped', round(r['kernel_ms_mean'],4), 'serial', round(r['serialized_launches']['kernel_ms_mean'],4), 'min', round(r['serialized_launches']['kernel_ms_min'],4), d['verified']['ok'])"
   done
 done
