@@ -205,6 +205,21 @@ def cpu_baseline_cfg1(states, signal, labels, length, reps=5):
     return t_seg, (time.perf_counter() - t0) / reps
 
 
+def cpu_baseline_features(data, frames, channel):
+    """Seconds the feature oracle (the reference's NumPy / SciPy calls, one core) takes for the amplitude + envelope
+    blocks and for the PSD block of ``data[:, channel]``."""
+    import warnings
+    from oracle import features_oracle as forc
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        forc.batch_features(data, frames, channel)
+        t1 = time.perf_counter()
+        forc.batch_psd_features(data, frames, channel)
+        t2 = time.perf_counter()
+    return t1 - t0, t2 - t1
+
+
 def cpu_baseline_cfg3(data, labels, frames):
     """CPU-baseline leg of BASELINE config 3 on a bounded sample: the oracle's 2D per-item loop."""
     import torch

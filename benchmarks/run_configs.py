@@ -328,6 +328,30 @@ def run(args, dev):
     emit("spec128/2D durratiomixup 4096 x 1 x 128 x 128 (268 MB in)", B5, ms, mn,
          4.0 * F5 * (2.0 * T5 * B5 + synth.mixed_samples(frames5, mix5)))
     resident_section(args, dev)
+    features_section(args, dev, cpu_legs)
+
+
+def features_section(args, dev, cpu_legs):
+    """The consumer side (train_model.py:519-532): classical features of an augmented batch, computed on the device."""
+    from pcgmix_b200 import features
+    rng = np.random.default_rng(synth.BENCH_SEED + 5)
+    B, C, L = 4096, 5, 2500                                    # the reference reads channel 4 of a five-row cycle
+    frames = synth.cycle_frames(rng, B, limit=L)
+    data = torch.from_numpy(synth.cycle_signals(rng, frames, (C,), L)).to(dev)
+    frames_dev = staging.upload([frames.astype(np.int32)], dev)[0]
+    out36 = torch.empty((B, 36), dtype=torch.float32, device=dev)
+    out80 = torch.empty((B, 80), dtype=torch.float32, device=dev)
+    legs = (("amplitude + Hilbert-envelope block (36 values)", lambda i: features.cycle_features(data, frames_dev, 4, out=out36)),
+            ("Welch-PSD block (80 values)", lambda i: features.cycle_psd_features(data, frames_dev, 4, out=out80)),
+            ("duration block (14 values)", lambda i: segmentation.duration_features(frames_dev, 1000)))
+    for name, fn in legs:
+        ms, mn = timed(fn, 20, warm=3)
+        emit("features/%s of 4096 cycles x 2500, one channel" % name, B, ms, mn)
+    if cpu_legs:
+        t_env, t_psd = bench.cpu_baseline_features(data[:64].cpu().numpy(), frames[:64], 4)
+        emit("features/CPU port (NumPy / SciPy calls of the reference, one core) on a 64-cycle sample: amplitude + envelope", 64,
+             t_env * 1e3, t_env * 1e3)
+        emit("features/CPU port on a 64-cycle sample: Welch-PSD block", 64, t_psd * 1e3, t_psd * 1e3)
 
 
 if __name__ == "__main__":

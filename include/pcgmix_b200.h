@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define PCGMIX_B200_VERSION 102
+#define PCGMIX_B200_VERSION 103
 
 /* bits OR-ed into *err_flag (device int32, may be NULL) by the kernels */
 #define PCGMIX_ERR_BAD_PARTNER   1   /* mix[b] outside [0,B): cycle copied unmixed          */
@@ -60,6 +60,7 @@ extern "C" {
 #define PCGMIX_ERR_EMPTY_STATE   32  /* a heart state without samples: features are NaN       */
 
 #define PCGMIX_CYCLE_FEATURES 36     /* floats per cycle written by pcgmix_cycle_features       */
+#define PCGMIX_CYCLE_PSD_FEATURES 80 /* floats per cycle written by pcgmix_cycle_psd_features   */
 
 #define PCGMIX_MAX_KNOT 30           /* largest `knot` of durmixmagwarp(sigma,knot) supported */
 
@@ -278,6 +279,25 @@ int pcgmix_mix1d_resident(const float* signal, int32_t n_rec, int32_t C, int32_t
 int pcgmix_cycle_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
                           int32_t L, int32_t channel, int32_t what, float* features, int32_t* err_flag,
                           pcgmix_stream_t stream);
+
+/*
+ * Power-spectral-density block of classical.feature_vector_seg (classical.py:358-643) for one channel of a
+ * batch of (augmented) cycles.  For the whole beat (data[:f4]), the systole (data[f1:f2]) and the diastole
+ * (data[f3:f4]), in this order, 26 values each:
+ *    +0      mean of scipy.signal.welch(segment, fs)'s PSD (Hann window of min(256, n) samples, half overlap,
+ *            mean removed per window, density scaling, one-sided, mean over the windows)
+ *    +1      mean of PSD / I, I = np.trapz(|hilbert(PSD)|, dx=5)
+ *    +2+2j   mean of the PSD over the bins with lo_j <= f <= hi_j   } bands 25-40, 40-60, 60-80, 80-100, 100-120,
+ *    +3+2j   mean of PSD / I over the same bins                     } 120-140, 140-160, 160-180, 180-200, 200-250,
+ *                                                                     250-300, 300-400 Hz; NaN for a band without bins
+ * then  78: round(mean(PSD/I) systole / RR, 4),  79: the same diastole / RR.  features [B][PCGMIX_CYCLE_PSD_FEATURES]
+ * fp32.  Agrees with SciPy's single-precision arithmetic to float32 rounding (tests: 2e-5 relative, NaN patterns
+ * identical).  A cycle with an empty beat, systole or diastole gets NaN features and raises PCGMIX_ERR_EMPTY_STATE
+ * (the reference raises).  fs > 0.
+ */
+int pcgmix_cycle_psd_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
+                              int32_t L, int32_t channel, int32_t fs, float* features, int32_t* err_flag,
+                              pcgmix_stream_t stream);
 
 /* 14 fp64 features per cycle from frames [n][5] int32 (stride `frame_stride` int32 between rows). */
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,

@@ -12,9 +12,13 @@ the same float32 data, so nothing is left to tolerance here).
 from __future__ import annotations
 
 import numpy as np
+from scipy import signal
 from scipy.signal import hilbert
 
 N_FEATURES = 36
+N_PSD_FEATURES = 80
+PSD_BANDS = ((25, 40), (40, 60), (60, 80), (80, 100), (100, 120), (120, 140), (140, 160), (160, 180), (180, 200), (200, 250),
+             (250, 300), (300, 400))
 
 
 def _round4(v):
@@ -61,6 +65,43 @@ def cycle_features(row: np.ndarray, frames) -> np.ndarray:
     out[34] = mean[3] / mean[2]
     out[35] = mean[0] / mean[2]
     return out
+
+
+def cycle_psd_features(row: np.ndarray, frames, fs: int = 1000) -> np.ndarray:
+    """The power-spectral-density block of ``feature_vector_seg`` (classical.py:358-643) for one cycle: for the whole
+    beat, the systole and the diastole — Welch PSD (SciPy defaults: Hann window of min(256, n) samples, half overlap,
+    mean removed per window, density scaling, one-sided, float32 arithmetic for float32 rows), the trapezoid integral
+    (dx = 5) of the Hilbert envelope of the PSD, then the mean of the PSD and of PSD / integral over all bins and over
+    the bins inside each of twelve closed frequency bands (an empty band gives NaN) — and two rounded ratios.
+    80 values, layout: ``pcgmix_cycle_psd_features`` in include/pcgmix_b200.h.  PARITY PIN:
+    tests/golden/cycle_psd_features.npz (the reference's statements executed verbatim), held bit-for-bit."""
+    row = np.asarray(row, dtype=np.float32)
+    f = [int(v) for v in frames[:5]]
+    out = np.zeros(N_PSD_FEATURES, np.float64)
+    norm_mean = []
+    for k, seg in enumerate((row[:f[4]], row[f[1]:f[2]], row[f[3]:f[4]])):            # RR, systole, diastole
+        freqs, psd = signal.welch(seg, fs)
+        integral = _np_trapz(np.abs(hilbert(psd)), 5)
+        normalized = psd / integral
+        base = 26 * k
+        out[base] = np.mean(psd)
+        out[base + 1] = np.mean(normalized)
+        norm_mean.append(np.mean(normalized))
+        for j, (lo, hi) in enumerate(PSD_BANDS):
+            inside = (lo <= freqs) & (freqs <= hi)
+            out[base + 2 + 2 * j] = np.mean(psd[inside])
+            out[base + 3 + 2 * j] = np.mean(normalized[inside])
+    out[78] = round(norm_mean[1] / norm_mean[0], 4)
+    out[79] = round(norm_mean[2] / norm_mean[0], 4)
+    return out
+
+
+def _np_trapz(y, dx):
+    return (np.trapz if hasattr(np, "trapz") else np.trapezoid)(y, dx=dx)
+
+
+def batch_psd_features(data: np.ndarray, frames: np.ndarray, channel: int, fs: int = 1000) -> np.ndarray:
+    return np.stack([cycle_psd_features(data[i, channel], frames[i], fs) for i in range(data.shape[0])])
 
 
 def batch_features(data: np.ndarray, frames: np.ndarray, channel: int) -> np.ndarray:

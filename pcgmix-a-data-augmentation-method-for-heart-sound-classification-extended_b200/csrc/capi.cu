@@ -435,6 +435,16 @@ int pcgmix_cycle_features(const float* x, const int32_t* frames, int32_t frame_s
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_cycle_features", e);
 }
 
+int pcgmix_cycle_psd_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C, int32_t L,
+                              int32_t channel, int32_t fs, float* features, int32_t* err_flag, pcgmix_stream_t stream) {
+    if (B < 0 || C <= 0 || L <= 0 || frame_stride < 5 || channel < 0 || channel >= C || fs <= 0) return fail("bad size argument");
+    if (B > 0 && (x == nullptr || frames == nullptr || features == nullptr)) return fail("null pointer argument");
+    forget_stream(static_cast<cudaStream_t>(stream));
+    const cudaError_t e = pcgmix::launch_cycle_psd_features(x, frames, frame_stride, B, C, L, channel, fs, features, err_flag,
+                                                            static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_cycle_psd_features", e);
+}
+
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs, double* features,
                              int32_t* err_flag, pcgmix_stream_t stream) {
     if (n < 0 || fs <= 0 || frame_stride < 5) return fail("bad size argument");

@@ -9,8 +9,11 @@ device kernels over the whole batch (one launch each, no D2H of the samples):
   amplitude block  classical.py:284-303  ->  :func:`cycle_features`, columns 0..9   (exact float32)
   envelope block   classical.py:305-360  ->  :func:`cycle_features`, columns 10..35 (float32 rounding)
 
-The Welch / wavelet / entropy blocks that follow in the reference are not provided.  Column names are the
-reference's variable names (:data:`FEATURE_NAMES`), so a caller can build the same table.
+  PSD block        classical.py:358-643  ->  :func:`cycle_psd_features`, 80 values  (float32 rounding)
+
+The blocks that follow in the reference (zero crossings, chroma, MFCC, wavelets, entropies: librosa, PyWavelets and
+antropy calls) are not provided.  Column names are the reference's variable names (:data:`FEATURE_NAMES`,
+:data:`PSD_FEATURE_NAMES`), so a caller can build the same table.
 """
 from __future__ import annotations
 
@@ -19,7 +22,8 @@ import torch
 
 from . import native, staging
 
-__all__ = ["FEATURE_NAMES", "DURATION_NAMES", "cycle_features", "classical_space_features"]
+__all__ = ["FEATURE_NAMES", "PSD_FEATURE_NAMES", "DURATION_NAMES", "cycle_features", "cycle_psd_features",
+           "classical_space_features"]
 
 _STATES = ("S1", "systole", "S2", "diastole")
 FEATURE_NAMES = tuple(
@@ -36,6 +40,14 @@ DURATION_NAMES = ("duration_RR", "BPM", "duration_S1", "duration_systole", "dura
                   "duration_ratio_systole_RR", "duration_ratio_S2_RR", "duration_ratio_diastole_RR",
                   "duration_ratio_systole_S1", "duration_ratio_diastole_S2")
 assert len(FEATURE_NAMES) == native.CYCLE_FEATURES
+PSD_BANDS = ((25, 40), (40, 60), (60, 80), (80, 100), (100, 120), (120, 140), (140, 160), (160, 180), (180, 200), (200, 250),
+             (250, 300), (300, 400))
+PSD_FEATURE_NAMES = tuple(
+    [name for s in ("RR", "systole", "diastole")
+     for name in [f"mean_psd_{s}", f"mean_psd_{s}_normalized"] +
+     [n for lo, hi in PSD_BANDS for n in (f"mean_psd_{s}_{lo}_{hi}_hz", f"mean_psd_{s}_normalized_{lo}_{hi}_hz")]] +
+    ["mean_psd_ratio_systole_RR", "mean_psd_ratio_diastole_RR"])
+assert len(PSD_FEATURE_NAMES) == native.CYCLE_PSD_FEATURES
 
 
 def _frames_on_device(frames, batch: int, device) -> torch.Tensor:
@@ -74,11 +86,35 @@ def cycle_features(data: torch.Tensor, frames, channel: int = 4, amplitude: bool
     return out
 
 
-def classical_space_features(data: torch.Tensor, frames, channel: int = 4, fs: int = 1000):
-    """Duration, amplitude and envelope blocks for a whole batch: ``(names, values)`` with ``values`` a
-    (B, 14 + 36) float64 device tensor in the reference's order of computation (durations first)."""
+def cycle_psd_features(data: torch.Tensor, frames, channel: int = 4, fs: int = 1000, out: torch.Tensor = None,
+                       err_flag: torch.Tensor = None) -> torch.Tensor:
+    """``(B, 80)`` float32 Welch-PSD features of ``data[:, channel]`` (layout: :data:`PSD_FEATURE_NAMES`): mean PSD and
+    mean normalised PSD of the whole beat, the systole and the diastole, overall and in twelve frequency bands (NaN for
+    a band that holds no bin of a short segment, like the reference), and the two ratios of classical.py:640-643.
+    Arguments as for :func:`cycle_features`; the reference calls Welch with ``Fs = 1000``.  There is no CPU path."""
+    if not isinstance(data, torch.Tensor) or not data.is_cuda:
+        raise RuntimeError("cycle_psd_features: data must be a CUDA tensor (there is no CPU fallback)")
+    if data.dim() != 3 or data.dtype != torch.float32:
+        raise ValueError("cycle_psd_features: data must be (B, C, L) float32")
+    if not 0 <= channel < data.shape[1]:
+        raise ValueError(f"channel {channel} outside the {data.shape[1]} channels of the batch")
+    if fs <= 0:
+        raise ValueError("fs must be positive")
+    data = data if data.is_contiguous() else data.contiguous()
+    if out is None:
+        out = torch.empty((data.shape[0], native.CYCLE_PSD_FEATURES), dtype=torch.float32, device=data.device)
+    native.cycle_psd_features(data, _frames_on_device(frames, data.shape[0], data.device), channel, fs, out, err_flag)
+    return out
+
+
+def classical_space_features(data: torch.Tensor, frames, channel: int = 4, fs: int = 1000, psd: bool = True):
+    """Duration, amplitude, envelope and (``psd``) PSD blocks for a whole batch: ``(names, values)`` with ``values`` a
+    (B, 14 + 36 [+ 80]) float64 device tensor in the reference's order of computation (durations first)."""
     from . import segmentation
     frames_dev = _frames_on_device(frames, data.shape[0], data.device)
     dur = segmentation.duration_features(frames_dev, fs)
     feats = cycle_features(data, frames_dev, channel)
-    return DURATION_NAMES + FEATURE_NAMES, torch.cat([dur, feats.to(torch.float64)], dim=1)
+    names, cols = DURATION_NAMES + FEATURE_NAMES, [dur, feats.to(torch.float64)]
+    if psd:
+        names, cols = names + PSD_FEATURE_NAMES, cols + [cycle_psd_features(data, frames_dev, channel, 1000).to(torch.float64)]
+    return names, torch.cat(cols, dim=1)

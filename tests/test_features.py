@@ -94,9 +94,12 @@ def test_features_of_an_augmented_batch_match_the_oracle():
     ohe = torch.nn.functional.one_hot(torch.from_numpy(labels), 2).to(dev)
     out, _, _, _ = augmentations.augment(Args, torch.from_numpy(x).to(dev), ohe, torch.from_numpy(frames), ["a"] * b, Step, None, dev, None)
     names, table = features.classical_space_features(out, torch.from_numpy(frames), channel=4)
-    assert len(names) == 50 and table.shape == (b, 50) and table.dtype == torch.float64
+    assert len(names) == 130 and table.shape == (b, 130) and table.dtype == torch.float64
     want = forc.batch_features(out.cpu().numpy(), frames, 4)
-    _check_block(table[:, 14:].cpu().numpy().astype(np.float32), want, 3)
+    _check_block(table[:, 14:50].cpu().numpy().astype(np.float32), want, 3)
+    _check_psd(table[:, 50:].cpu().numpy(), forc.batch_psd_features(out.cpu().numpy(), frames, 4))
+    names50, table50 = features.classical_space_features(out, torch.from_numpy(frames), channel=4, psd=False)
+    assert len(names50) == 50 and torch.equal(table50, table[:, :50])
     assert table[0, 0].item() == int(frames[0, 4] * 1000 / 1000)          # duration_RR in ms
 
 
@@ -121,3 +124,99 @@ def test_nan_propagates_like_np_max():
     want = forc.cycle_features(x[0, 0].cpu().numpy(), frames[0].numpy())
     assert np.isnan(out[1]) and np.isnan(want[1]) and out[0] == want[0] and out[2] == want[2]
     assert np.array_equal(np.isnan(out[:10]), np.isnan(want[:10]))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PSD block (classical.py:358-643): Welch PSD of the beat, the systole and the diastole, envelope integral of the
+# spectrum, overall and band means, two ratios.  SciPy: single-precision FFTs; the kernel: direct float64 sums over
+# float32 windows.  2e-5 relative on the means, one unit of the last decimal on the two rounded ratios, identical NaNs.
+
+def _check_psd(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape and got.shape[1] == 80
+    assert np.array_equal(np.isnan(got), np.isnan(want)), "NaN pattern (empty bands, one-sample segments) must be the reference's"
+    ok = ~np.isnan(want)
+    means = np.ones(80, bool)
+    means[78:] = False
+    sel = ok & means[None, :]
+    err = np.abs(got[sel] - want[sel]) / np.maximum(np.abs(want[sel]), 1e-30)
+    err[want[sel] == 0] = np.abs(got[sel])[want[sel] == 0]
+    assert err.max() <= REL, float(err.max())
+    sel = ok & ~means[None, :]
+    step = np.abs(got[sel] - want[sel])
+    assert (step <= 1.0001e-4 + REL * np.abs(want[sel])).all(), float(step.max())
+
+
+def test_psd_oracle_matches_reference_statements_bitwise(golden):
+    import warnings
+    g = golden("cycle_psd_features")
+    assert g["features"].shape == (64, 80) and len(g["names"]) == 80
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                       # SciPy warns about windows longer than a short segment, NumPy about empty bands
+        for i in range(g["data"].shape[0]):
+            got = forc.cycle_psd_features(g["data"][i], g["frames"][i])
+            want = g["features"][i]
+            assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)]), i
+    assert np.isnan(g["features"]).any(), "the fixture must hold short segments with empty bands"
+
+
+def test_psd_feature_names_are_the_reference_variable_names(golden):
+    from pcgmix_b200 import features
+    assert [str(n) for n in golden("cycle_psd_features")["names"]] == list(features.PSD_FEATURE_NAMES)
+
+
+def test_psd_cpu_tensor_is_refused():
+    from pcgmix_b200 import features
+    with pytest.raises(RuntimeError):
+        features.cycle_psd_features(torch.zeros(2, 5, 100), torch.zeros(2, 5, dtype=torch.int64))
+
+
+@pytest.mark.gpu
+def test_psd_kernel_vs_reference_fixture(golden):
+    from pcgmix_b200 import features
+    g = golden("cycle_psd_features")
+    data = torch.from_numpy(np.ascontiguousarray(g["data"][:, None, :])).cuda()          # (B, 1, L)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = features.cycle_psd_features(data, torch.from_numpy(g["frames"]), channel=0, err_flag=err)
+    assert out.shape == (64, 80) and out.dtype == torch.float32 and int(err.item()) == 0
+    _check_psd(out.cpu().numpy(), g["features"])
+
+
+@pytest.mark.gpu
+def test_psd_kernel_on_a_strided_channel_and_device_frames(golden):
+    from pcgmix_b200 import features
+    g = golden("cycle_psd_features")
+    rng = np.random.default_rng(3)
+    batch = rng.standard_normal((64, 5, 2500)).astype(np.float32)
+    batch[:, 4] = g["data"]
+    frames_dev = torch.from_numpy(g["frames"].astype(np.int32)).cuda()
+    out = features.cycle_psd_features(torch.from_numpy(batch).cuda(), frames_dev, channel=4)
+    _check_psd(out.cpu().numpy(), g["features"])
+
+
+@pytest.mark.gpu
+def test_psd_empty_segment_gives_nan_and_a_flag():
+    from pcgmix_b200 import features, native
+    x = torch.randn(3, 1, 600, device="cuda")
+    frames = torch.tensor([[0, 100, 300, 380, 590], [0, 100, 100, 180, 590], [0, 100, 300, 380, 380]])     # empty systole; empty diastole
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = features.cycle_psd_features(x, frames, channel=0, err_flag=err).cpu().numpy()
+    assert int(err.item()) == native.ERR_EMPTY_STATE
+    assert np.isfinite(out[0, :2]).all() and np.isnan(out[1]).all() and np.isnan(out[2]).all()
+    want = forc.cycle_psd_features(x[0, 0].cpu().numpy(), frames[0].numpy())
+    _check_psd(out[:1], want[None])
+
+
+@pytest.mark.gpu
+def test_psd_other_sampling_rate_moves_the_bands():
+    """``fs`` is the reference's ``Fs`` argument of ``signal.welch``: at 2 kHz the bins are twice as far apart."""
+    import warnings
+    from pcgmix_b200 import features
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((4, 1, 3000)).astype(np.float32)
+    frames = np.array([[0, 200, 700, 900, 2400], [0, 250, 760, 1000, 2999], [0, 180, 436, 600, 1500], [0, 300, 555, 800, 2000]])
+    out = features.cycle_psd_features(torch.from_numpy(x).cuda(), torch.from_numpy(frames), channel=0, fs=2000).cpu().numpy()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.stack([forc.cycle_psd_features(x[i, 0], frames[i], 2000) for i in range(4)])
+    _check_psd(out, want)
