@@ -22,9 +22,8 @@
 // Hilbert kernel
 //     N even:  h[m] = (2/N) cot(pi m / N) for odd m, 0 for even m
 //     N odd :  h[m] = (1/N) (cos(pi m / N) - (-1)^m) / sin(pi m / N)
-// which is evaluated here directly (O(N^2) FMAs per segment out of shared memory: 1.7 M per cycle, 1.7 ms for a
-// 4096-cycle batch — bound by the two shared-memory loads per FMA; the reference's SciPy calls take 0.4 ms per
-// cycle on one host core).  Both are float32 computations of the same quantity with different rounding
+// which is evaluated here directly (O(N^2) FMAs per segment out of shared memory: 1.7 M per cycle, 0.55 ms for a
+// 4096-cycle batch; the reference's SciPy calls take 0.4 ms per cycle on one host core).  Both are float32 computations of the same quantity with different rounding
 // orders, so parity is a tolerance (tests: 2e-5 relative on integrals and means, one unit of the fourth
 // decimal on the rounded ratios), not bit equality.
 //
@@ -40,7 +39,10 @@ namespace pcgmix {
 namespace {
 
 constexpr int kFeatThreads = 256;
-constexpr int kTile = 4;               // envelope outputs per thread and pass
+constexpr int kTile = 9;               // envelope outputs per thread and pass: ADJACENT samples, so that a thread's taps slide
+                                       // over one register window; odd, so that the threads of a warp (9 floats apart) hit
+                                       // 32 different banks
+constexpr int kGuard = 2 * kTile;      // floats of zeroed slack in front of / behind the staged segment and behind the kernel
 
 __device__ __forceinline__ float round4(float v) {      // NumPy's round(float32, 4)
     return __fdiv_rn(rintf(__fmul_rn(v, 10000.0f)), 10000.0f);
@@ -153,12 +155,13 @@ __global__ void __launch_bounds__(kFeatThreads) cycle_features_kernel(const __gr
 
     if (a.what & 2) {
         // ---- envelope block ---------------------------------------------------------------------------------
-        // shared memory: xs[2N] (the segment twice, so that (n - m) mod N is a plain offset), hs[N] (Hilbert
-        // kernel), es[N] (envelope); N <= c[4] <= L
+        // shared memory: [guard] xs[2N] [guard] (the segment twice, so that (n - m) mod N is a plain offset), hs[N] [guard]
+        // (Hilbert kernel, zero behind tap N - 1), es[N] (envelope); N <= c[4] <= L.  The guards are zero: taps past
+        // N - 1 multiply them with a zero kernel value, and 0 * garbage could be NaN.
         const int cap = c[4];
-        float* xs = smem;
-        float* hs = xs + 2 * cap;
-        float* es = hs + cap;
+        float* xs = smem + kGuard;
+        float* hs = xs + 2 * cap + kGuard;
+        float* es = hs + cap + kGuard;
         float integral[5], mean[5];
 #pragma unroll 1
         for (int s = 0; s < 5; ++s) {
@@ -180,24 +183,50 @@ __global__ void __launch_bounds__(kFeatThreads) cycle_features_kernel(const __gr
                 }
                 hs[t] = h;
             }
+            if (threadIdx.x < kGuard) {
+                xs[-1 - static_cast<int>(threadIdx.x)] = 0.0f;
+                xs[2 * N + threadIdx.x] = 0.0f;
+                hs[N + threadIdx.x] = 0.0f;
+            }
             __syncthreads();
-            const int m_step = (N & 1) ? 1 : 2;          // even N: only odd taps are non-zero
-            for (int base = threadIdx.x; base < N; base += kFeatThreads * kTile) {
+            // Hx[n] = sum_m h[m] x[(n - m) mod N], taps in ascending m.  A thread owns kTile adjacent outputs; a chunk of
+            // kTile taps (every tap for odd N, the odd ones for even N — the even ones are zero) needs one contiguous
+            // window of the segment in registers: 2 kTile - 1 (3 kTile - 2) shared loads and kTile broadcast loads of the
+            // kernel for kTile^2 FMAs, instead of five loads per four.
+            for (int first = kTile * threadIdx.x; first < N; first += kTile * kFeatThreads) {
                 float acc[kTile];
-                int idx[kTile];
+#pragma unroll
+                for (int j = 0; j < kTile; ++j) acc[j] = 0.0f;
+                if (N & 1) {
+                    for (int m = 1; m < N; m += kTile) {
+                        const float* src = xs + (first + N - m - (kTile - 1));
+                        float w[2 * kTile - 1];
+#pragma unroll
+                        for (int i = 0; i < 2 * kTile - 1; ++i) w[i] = src[i];
+#pragma unroll
+                        for (int u = 0; u < kTile; ++u) {
+                            const float h = hs[m + u];
+#pragma unroll
+                            for (int j = 0; j < kTile; ++j) acc[j] = fmaf(h, w[(kTile - 1) + j - u], acc[j]);
+                        }
+                    }
+                } else {
+                    for (int m = 1; m < N; m += 2 * kTile) {
+                        const float* src = xs + (first + N - m - 2 * (kTile - 1));
+                        float w[3 * kTile - 2];
+#pragma unroll
+                        for (int i = 0; i < 3 * kTile - 2; ++i) w[i] = src[i];
+#pragma unroll
+                        for (int u = 0; u < kTile; ++u) {
+                            const float h = hs[m + 2 * u];
+#pragma unroll
+                            for (int j = 0; j < kTile; ++j) acc[j] = fmaf(h, w[2 * (kTile - 1) + j - 2 * u], acc[j]);
+                        }
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < kTile; ++j) {
-                    acc[j] = 0.0f;
-                    idx[j] = min(base + j * kFeatThreads, N - 1) + N;      // (clamped lanes compute a duplicate, not stored)
-                }
-                for (int m = 1; m < N; m += m_step) {
-                    const float h = hs[m];
-#pragma unroll
-                    for (int j = 0; j < kTile; ++j) acc[j] = fmaf(h, xs[idx[j] - m], acc[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < kTile; ++j) {
-                    const int n = base + j * kFeatThreads;
+                    const int n = first + j;
                     if (n < N) {
                         const float re = xs[n];
                         es[n] = sqrtf(fmaf(re, re, acc[j] * acc[j]));
@@ -246,7 +275,7 @@ cudaError_t launch_cycle_features(const float* x, const int32_t* frames, int32_t
                                   cudaStream_t stream) {
     if (B == 0) return cudaSuccess;
     FeatArgs a{x, frames, frame_stride, B, C, L, channel, features, err, what};
-    const size_t smem = (what & 2) ? static_cast<size_t>(L) * 4 * sizeof(float) : 0;
+    const size_t smem = (what & 2) ? (static_cast<size_t>(L) * 4 + 3 * kGuard) * sizeof(float) : 0;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     if (smem > 48 * 1024) {
         // (per device and cheap: set every time rather than remembered per device)

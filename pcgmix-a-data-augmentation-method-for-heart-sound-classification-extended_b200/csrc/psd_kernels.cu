@@ -18,7 +18,7 @@
 // thread k accumulates bin k over the window out of shared memory, rotating its twiddle by one complex
 // multiplication per sample (re-seeded from a table of the nper twiddles every 64 samples), in float64 — 33 k
 // complex FMAs per window, ~11 windows per cycle — and no FFT plan per segment length is needed (systoles are
-// shorter than 256 samples, so nearly every cycle has its own transform length).  1.3 ms for 4096 cycles (the
+// shorter than 256 samples, so nearly every cycle has its own transform length).  1.2 ms for 4096 cycles (the
 // reference's SciPy calls: 1.2 ms per cycle on one host core).  The Hilbert envelope of the spectrum is the circular
 // convolution with the discrete Hilbert kernel (see feature_kernels.cu), again direct.
 //
