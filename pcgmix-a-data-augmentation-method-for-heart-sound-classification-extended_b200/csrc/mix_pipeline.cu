@@ -65,8 +65,8 @@ namespace {
 #endif
 
 #ifdef PCGMIX_PROFILING
-// per-CTA {first instruction, first item consumed, last store done} in globaltimer nanoseconds, last launch only
-__device__ unsigned long long g_timeline[3 * 2048];
+// per-CTA {first instruction, first item consumed, last store done} in globaltimer nanoseconds and the SM it ran on, last launch only
+__device__ unsigned long long g_timeline[4 * 2048];
 __device__ __forceinline__ unsigned long long global_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -75,7 +75,8 @@ __device__ __forceinline__ unsigned long long global_ns() {
 #endif
 
 constexpr int kMaxStages = 8;
-constexpr int kResidentStages = 6;      // RESIDENT default: two CTAs per SM (registers), six stages each fill the shared memory
+constexpr int kResidentStages = 6;      // RESIDENT default: two CTAs per SM (registers); up to six stages each, fewer when the
+                                        // slices are long (the launcher keeps two CTAs per SM)
 constexpr int kHeaderBytes = 1024;
 constexpr int kProducerWarps = 2;       // producer warps take alternate items (one warp's instruction stream per
                                         // item, ~600 dependent instructions with the spline set-up, was the bound)
@@ -271,7 +272,12 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
         if constexpr (MAGWARP) next = warm(a.knots, static_cast<long long>(a.B) * (a.K + 2) * a.R * 8, next);
     }
 #ifdef PCGMIX_PROFILING
-    if (threadIdx.x == 0 && blockIdx.x < 2048) g_timeline[3 * blockIdx.x] = global_ns();
+    if (threadIdx.x == 0 && blockIdx.x < 2048) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_timeline[4 * blockIdx.x] = global_ns();
+        g_timeline[4 * blockIdx.x + 3] = smid;
+    }
 #endif
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
@@ -668,7 +674,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
             }
             bulk_store_wait_all();                         // every result is in global memory before exit
 #ifdef PCGMIX_PROFILING
-            if (blockIdx.x < 2048) g_timeline[3 * blockIdx.x + 2] = global_ns();
+            if (blockIdx.x < 2048) g_timeline[4 * blockIdx.x + 2] = global_ns();
 #endif
         }
     } else {
@@ -708,7 +714,7 @@ mix_pipeline_kernel(const __grid_constant__ MixArgs a, const __grid_constant__ P
                 mbar_wait(&full[stage], phase);
             }
 #ifdef PCGMIX_PROFILING
-            if (it == 0 && ct == 0 && blockIdx.x < 2048) g_timeline[3 * blockIdx.x + 1] = global_ns();
+            if (it == 0 && ct == 0 && blockIdx.x < 2048) g_timeline[4 * blockIdx.x + 1] = global_ns();
 #endif
 
             const int lo1 = meta->win[1].x, lo2 = meta->win[2].x, lo3 = meta->win[3].x;
@@ -976,7 +982,7 @@ cudaError_t launch_nct(const MixArgs& a, const PipeArgs& pa, size_t smem, int wa
 
 #ifdef PCGMIX_PROFILING
 cudaError_t read_timeline(unsigned long long* host, int n_ctas) {
-    return cudaMemcpyFromSymbol(host, g_timeline, sizeof(unsigned long long) * 3 * static_cast<size_t>(n_ctas > 2048 ? 2048 : n_ctas));
+    return cudaMemcpyFromSymbol(host, g_timeline, sizeof(unsigned long long) * 4 * static_cast<size_t>(n_ctas > 2048 ? 2048 : n_ctas));
 }
 #endif
 
@@ -1026,6 +1032,12 @@ cudaError_t launch_mix_pipeline(const MixArgs& base, bool magwarp, const Pipelin
     if (n_items > 2147483647LL) return cudaErrorInvalidConfiguration;
     pa.n_items = static_cast<int>(n_items);
     pa.header_bytes = static_cast<int>((kHeaderBytes + mat_bytes + 127) & ~static_cast<size_t>(127));
+    if (resident && tune.stages <= 0) {
+        // RESIDENT default: as many stages (at most kResidentStages) as still let two CTAs share an SM
+        const size_t per_cta = (228 * 1024) / 2 - 1024 - pa.header_bytes;
+        const int fit = static_cast<int>(per_cta / static_cast<size_t>(pa.stage_bytes));
+        pa.stages = fit < kResidentProducerWarps ? kResidentProducerWarps : (fit < kResidentStages ? fit : kResidentStages);
+    }
     const size_t smem = pa.header_bytes + static_cast<size_t>(pa.stages) * pa.stage_bytes;
     if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
     pa.debug = tune.debug;                                  // (the kernel reads it only in a PCGMIX_PROFILING build)
