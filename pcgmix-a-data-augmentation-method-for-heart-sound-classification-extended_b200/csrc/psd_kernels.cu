@@ -14,12 +14,11 @@
 //
 // then round(mean normalized systole / RR, 4) and the same for the diastole: 80 values per cycle.
 //
-// One CTA per cycle.  A window is at most 256 samples, so its spectrum (at most 129 bins) is evaluated directly:
-// thread k accumulates bin k over the window out of shared memory, rotating its twiddle by one complex
-// multiplication per sample (re-seeded from a table of the nper twiddles every 64 samples), in float64 — 33 k
-// complex FMAs per window, ~11 windows per cycle — and no FFT plan per segment length is needed (systoles are
-// shorter than 256 samples, so nearly every cycle has its own transform length).  1.2 ms for 4096 cycles (the
-// reference's SciPy calls: 1.2 ms per cycle on one host core).  The Hilbert envelope of the spectrum is the circular
+// One CTA per cycle, float64 transforms.  Full windows (256 samples: all windows of a segment that is at least that
+// long) go through a radix-2 FFT in shared memory.  A shorter segment is a single window of its own length (systoles
+// nearly always: every cycle has its own transform length), and its spectrum (at most 128 bins) is evaluated
+// directly: thread k accumulates bin k over the window, rotating its twiddle by one complex multiplication per
+// sample (re-seeded from a table of the nper twiddles every 64 samples) — no FFT plan per length.  The Hilbert envelope of the spectrum is the circular
 // convolution with the discrete Hilbert kernel (see feature_kernels.cu), again direct.
 //
 // Numerics.  SciPy computes all of this in float32 for float32 cycles (single-precision pocketfft).  Here the
@@ -89,6 +88,7 @@ __device__ __forceinline__ float hann(int t, int n) {
 __global__ void __launch_bounds__(kPsdThreads) cycle_psd_kernel(const __grid_constant__ PsdArgs a) {
     __shared__ double2 s_tw[kMaxWindow];         // (cos, sin)(2 pi j / nper)
     __shared__ double s_y[kMaxWindow];           // the window: (x - mean) * w, rounded to float32 like the reference's
+    __shared__ double2 s_f[kMaxWindow];          // a full window's FFT, in place
     __shared__ double s_acc[kMaxBins];           // sum of the windows' spectra
     __shared__ float s_psd[kMaxBins];
     __shared__ float s_norm[kMaxBins];
@@ -144,7 +144,36 @@ __global__ void __launch_bounds__(kPsdThreads) cycle_psd_kernel(const __grid_con
         for (int wdx = 0; wdx < nseg; ++wdx) {
             const float v = tid < nper ? __ldg(row + beg[s] + wdx * step + tid) : 0.0f;
             const float mean = static_cast<float>(block_sum(static_cast<double>(v), s_red) / static_cast<double>(nper));
-            if (tid < nper) s_y[tid] = static_cast<double>(__fmul_rn(__fsub_rn(v, mean), w_mine));
+            const double y_mine = static_cast<double>(__fmul_rn(__fsub_rn(v, mean), w_mine));
+            if (nper == kMaxWindow) {
+                // a full window (all but the short segments' single one): radix-2 FFT of the 256 real samples in shared
+                // memory, float64 — 8 passes of 128 butterflies against 129 bins x 256 samples of the direct sum below
+                s_f[__brev(static_cast<unsigned>(tid)) >> 24] = make_double2(y_mine, 0.0);
+                __syncthreads();
+#pragma unroll 1
+                for (int half = 1; half < kMaxWindow; half <<= 1) {
+                    if (tid < kMaxWindow / 2) {
+                        const int j = tid & (half - 1);
+                        const int i0 = ((tid - j) << 1) + j;
+                        const double2 tw = s_tw[j * (kMaxWindow / 2 / half)];      // e^(-2 pi i j / (2 half)) = (tw.x, -tw.y)
+                        const double2 lo = s_f[i0], hi = s_f[i0 + half];
+                        const double tr = hi.x * tw.x + hi.y * tw.y;
+                        const double ti = hi.y * tw.x - hi.x * tw.y;
+                        s_f[i0] = make_double2(lo.x + tr, lo.y + ti);
+                        s_f[i0 + half] = make_double2(lo.x - tr, lo.y - ti);
+                    }
+                    __syncthreads();
+                }
+                if (tid < M) {
+                    const double2 X = s_f[tid];
+                    double p = (X.x * X.x + X.y * X.y) * scale;
+                    if (tid > 0 && tid < M - 1) p *= 2.0;          // not DC, not the Nyquist bin
+                    s_acc[tid] += p;
+                }
+                __syncthreads();
+                continue;
+            }
+            if (tid < nper) s_y[tid] = y_mine;
             __syncthreads();
             if (tid < M) {
                 // bin `tid`: sum_t y[t] e^(-2 pi i tid t / nper); the twiddle advances by one complex multiplication per
