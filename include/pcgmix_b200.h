@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define PCGMIX_B200_VERSION 103
+#define PCGMIX_B200_VERSION 104
 
 /* bits OR-ed into *err_flag (device int32, may be NULL) by the kernels */
 #define PCGMIX_ERR_BAD_PARTNER   1   /* mix[b] outside [0,B): cycle copied unmixed          */
@@ -61,6 +61,7 @@ extern "C" {
 
 #define PCGMIX_CYCLE_FEATURES 36     /* floats per cycle written by pcgmix_cycle_features       */
 #define PCGMIX_CYCLE_PSD_FEATURES 80 /* floats per cycle written by pcgmix_cycle_psd_features   */
+#define PCGMIX_CYCLE_MOMENT_FEATURES 10 /* floats per cycle written by pcgmix_cycle_moment_features */
 
 #define PCGMIX_MAX_KNOT 30           /* largest `knot` of durmixmagwarp(sigma,knot) supported */
 
@@ -298,6 +299,17 @@ int pcgmix_cycle_features(const float* x, const int32_t* frames, int32_t frame_s
 int pcgmix_cycle_psd_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
                               int32_t L, int32_t channel, int32_t fs, float* features, int32_t* err_flag,
                               pcgmix_stream_t stream);
+
+/*
+ * Skewness / kurtosis block of classical.feature_vector_seg (classical.py:893-905): scipy.stats.skew (0..4) and
+ * scipy.stats.kurtosis (5..9; biased, Fisher) of RR = data[:f4], S1 = data[:f1], systole, S2, diastole of one channel of
+ * every cycle.  features [B][PCGMIX_CYCLE_MOMENT_FEATURES] fp32; float32 arithmetic like SciPy's for float32 rows (tests:
+ * 2e-5 relative + 2e-6 absolute); NaN for a segment without variance like there.  An empty segment gets NaN and raises
+ * PCGMIX_ERR_EMPTY_STATE.
+ */
+int pcgmix_cycle_moment_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
+                                 int32_t L, int32_t channel, float* features, int32_t* err_flag,
+                                 pcgmix_stream_t stream);
 
 /* 14 fp64 features per cycle from frames [n][5] int32 (stride `frame_stride` int32 between rows). */
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,

@@ -96,6 +96,21 @@ def cycle_psd_features(row: np.ndarray, frames, fs: int = 1000) -> np.ndarray:
     return out
 
 
+def cycle_moment_features(row: np.ndarray, frames) -> np.ndarray:
+    """The skewness / kurtosis block of ``feature_vector_seg`` (classical.py:893-905): ``scipy.stats.skew`` and
+    ``scipy.stats.kurtosis`` (biased, Fisher) of RR, S1, systole, S2, diastole — 10 values, float32 arithmetic for float32
+    rows.  PARITY PIN: tests/golden/cycle_moment_features.npz (the reference's statements executed verbatim), bit-for-bit."""
+    from scipy import stats
+    row = np.asarray(row, dtype=np.float32)
+    f = [int(v) for v in frames[:5]]
+    seg = [row[:f[4]], row[:f[1]], row[f[1]:f[2]], row[f[2]:f[3]], row[f[3]:f[4]]]
+    return np.array([stats.skew(s) for s in seg] + [stats.kurtosis(s) for s in seg], dtype=np.float64)
+
+
+def batch_moment_features(data: np.ndarray, frames: np.ndarray, channel: int) -> np.ndarray:
+    return np.stack([cycle_moment_features(data[i, channel], frames[i]) for i in range(data.shape[0])])
+
+
 def _np_trapz(y, dx):
     return (np.trapz if hasattr(np, "trapz") else np.trapezoid)(y, dx=dx)
 

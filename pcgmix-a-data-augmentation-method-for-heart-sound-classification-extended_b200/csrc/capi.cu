@@ -445,6 +445,16 @@ int pcgmix_cycle_psd_features(const float* x, const int32_t* frames, int32_t fra
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_cycle_psd_features", e);
 }
 
+int pcgmix_cycle_moment_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C, int32_t L,
+                                 int32_t channel, float* features, int32_t* err_flag, pcgmix_stream_t stream) {
+    if (B < 0 || C <= 0 || L <= 0 || frame_stride < 5 || channel < 0 || channel >= C) return fail("bad size argument");
+    if (B > 0 && (x == nullptr || frames == nullptr || features == nullptr)) return fail("null pointer argument");
+    forget_stream(static_cast<cudaStream_t>(stream));
+    const cudaError_t e = pcgmix::launch_cycle_moment_features(x, frames, frame_stride, B, C, L, channel, features, err_flag,
+                                                               static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_cycle_moment_features", e);
+}
+
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs, double* features,
                              int32_t* err_flag, pcgmix_stream_t stream) {
     if (n < 0 || fs <= 0 || frame_stride < 5) return fail("bad size argument");

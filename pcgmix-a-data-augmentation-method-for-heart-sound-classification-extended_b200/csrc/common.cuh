@@ -141,6 +141,8 @@ cudaError_t launch_cycle_features(const float* x, const int32_t* frames, int32_t
 cudaError_t launch_cycle_psd_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
                                       int32_t L, int32_t channel, int32_t fs, float* features, int32_t* err,
                                       cudaStream_t stream);
+cudaError_t launch_cycle_moment_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
+                                         int32_t L, int32_t channel, float* features, int32_t* err, cudaStream_t stream);
 cudaError_t launch_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,
                                      double* features, int32_t* err, cudaStream_t stream);
 

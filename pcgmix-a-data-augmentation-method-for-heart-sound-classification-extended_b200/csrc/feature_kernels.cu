@@ -10,9 +10,11 @@
 //                                            beat; np.trapz(dx=5) integrals, eight rounded integral ratios,
 //                                            five means, eight mean ratios
 //
+//   moments block   (classical.py:893-905)   scipy.stats.skew / kurtosis of the whole beat and the four states
+//                                            (cycle_moments_kernel, at the end of this file)
+//
 // (the duration block, :248-283, is pcgmix_duration_features in segment_kernels.cu; the Welch-PSD block, :358-643,
-// is pcgmix_cycle_psd_features in psd_kernels.cu; the librosa / PyWavelets / antropy blocks behind it are not
-// provided).
+// is pcgmix_cycle_psd_features in psd_kernels.cu; the librosa / PyWavelets / antropy blocks are not provided).
 //
 // Numerics.  The reference works on float32 cycles, so every quantity above is float32 there.  Amplitude block:
 // exact — a maximum is a selection, NaN propagates like np.max, and NumPy's round(x, 4) on a float32 scalar is
@@ -268,7 +270,84 @@ __global__ void __launch_bounds__(kFeatThreads) cycle_features_kernel(const __gr
     }
 }
 
+// Skewness / kurtosis block (classical.py:893-905): scipy.stats.skew and scipy.stats.kurtosis (biased estimators, Fisher's
+// definition) of the whole beat and the four states.  One warp per segment: the mean, then the second, third and fourth
+// central moments.  The reference's float32 arithmetic is followed where it matters — the mean and the deviations
+// x - mean are float32, the powers are float32 products ((d*d)*d, (d*d)*(d*d), as SciPy's exponentiation by squaring forms
+// them) — and only the sums are carried in float64 instead of NumPy's pairwise float32; a segment whose variance is not
+// above (eps * mean)^2 gives NaN like there.  Tests: 2e-5 relative + 2e-6 absolute (a skewness near zero is a difference
+// of large terms in both implementations).
+struct MomentArgs {
+    const float* x;
+    const int32_t* frames;
+    int32_t frame_stride;
+    int32_t B, C, L, channel;
+    float* features;
+    int32_t* err;
+};
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(160) cycle_moments_kernel(const __grid_constant__ MomentArgs a) {
+    const int b = blockIdx.x;
+    const int s = threadIdx.x >> 5;                      // segment: RR, S1, systole, S2, diastole
+    const int lane = threadIdx.x & 31;
+    const float* __restrict__ row = a.x + (static_cast<size_t>(b) * a.C + a.channel) * a.L;
+    float* __restrict__ out = a.features + static_cast<size_t>(b) * PCGMIX_CYCLE_MOMENT_FEATURES;
+    int c[5];
+    bool sane = true;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int f = __ldg(a.frames + static_cast<size_t>(b) * a.frame_stride + k);
+        sane = sane && f >= 0;
+        c[k] = min(max(f, 0), a.L);
+    }
+    const int beg = s == 0 || s == 1 ? 0 : c[s - 1];
+    const int end = s == 0 ? c[4] : c[s];
+    const int n = end - beg;
+    if (!sane || n <= 0) {
+        if (lane == 0) {
+            out[s] = out[5 + s] = __int_as_float(0x7fc00000);
+            if (a.err != nullptr) atomicOr(a.err, static_cast<int>(PCGMIX_ERR_EMPTY_STATE));
+        }
+        return;
+    }
+    double sum = 0.0;
+    for (int t = lane; t < n; t += 32) sum += static_cast<double>(__ldg(row + beg + t));
+    const float mean = static_cast<float>(warp_sum_f64(sum) / static_cast<double>(n));
+    double s2 = 0.0, s3 = 0.0, s4 = 0.0;
+    for (int t = lane; t < n; t += 32) {
+        const float d = __fsub_rn(__ldg(row + beg + t), mean);
+        const float d2 = __fmul_rn(d, d);
+        s2 += static_cast<double>(d2);
+        s3 += static_cast<double>(__fmul_rn(d2, d));
+        s4 += static_cast<double>(__fmul_rn(d2, d2));
+    }
+    const float m2 = static_cast<float>(warp_sum_f64(s2) / static_cast<double>(n));
+    const float m3 = static_cast<float>(warp_sum_f64(s3) / static_cast<double>(n));
+    const float m4 = static_cast<float>(warp_sum_f64(s4) / static_cast<double>(n));
+    if (lane == 0) {
+        const float tiny = __fmul_rn(1.1920928955078125e-07f, mean);            // float32 eps * mean
+        const bool flat = m2 <= __fmul_rn(tiny, tiny);
+        const float not_a_number = __int_as_float(0x7fc00000);
+        out[s] = flat ? not_a_number : __fdiv_rn(m3, static_cast<float>(pow(static_cast<double>(m2), 1.5)));
+        out[5 + s] = flat ? not_a_number : __fsub_rn(__fdiv_rn(m4, __fmul_rn(m2, m2)), 3.0f);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_cycle_moment_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
+                                         int32_t L, int32_t channel, float* features, int32_t* err, cudaStream_t stream) {
+    if (B == 0) return cudaSuccess;
+    MomentArgs a{x, frames, frame_stride, B, C, L, channel, features, err};
+    cycle_moments_kernel<<<static_cast<unsigned>(B), 160, 0, stream>>>(a);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_cycle_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
                                   int32_t L, int32_t channel, int32_t what, float* features, int32_t* err,

@@ -10,9 +10,10 @@ device kernels over the whole batch (one launch each, no D2H of the samples):
   envelope block   classical.py:305-360  ->  :func:`cycle_features`, columns 10..35 (float32 rounding)
 
   PSD block        classical.py:358-643  ->  :func:`cycle_psd_features`, 80 values  (float32 rounding)
+  moments block    classical.py:893-905  ->  :func:`cycle_moment_features`, 10 values (float32 rounding)
 
-The blocks that follow in the reference (zero crossings, chroma, MFCC, wavelets, entropies: librosa, PyWavelets and
-antropy calls) are not provided.  Column names are the reference's variable names (:data:`FEATURE_NAMES`,
+The blocks between and behind those in the reference (zero crossings, chroma, RMS, spectral statistics, MFCC, wavelets,
+entropies: librosa, PyWavelets and antropy calls) are not provided.  Column names are the reference's variable names (:data:`FEATURE_NAMES`,
 :data:`PSD_FEATURE_NAMES`), so a caller can build the same table.
 """
 from __future__ import annotations
@@ -22,8 +23,8 @@ import torch
 
 from . import native, staging
 
-__all__ = ["FEATURE_NAMES", "PSD_FEATURE_NAMES", "DURATION_NAMES", "cycle_features", "cycle_psd_features",
-           "classical_space_features"]
+__all__ = ["FEATURE_NAMES", "PSD_FEATURE_NAMES", "MOMENT_FEATURE_NAMES", "DURATION_NAMES", "cycle_features",
+           "cycle_psd_features", "cycle_moment_features", "classical_space_features"]
 
 _STATES = ("S1", "systole", "S2", "diastole")
 FEATURE_NAMES = tuple(
@@ -48,6 +49,8 @@ PSD_FEATURE_NAMES = tuple(
      [n for lo, hi in PSD_BANDS for n in (f"mean_psd_{s}_{lo}_{hi}_hz", f"mean_psd_{s}_normalized_{lo}_{hi}_hz")]] +
     ["mean_psd_ratio_systole_RR", "mean_psd_ratio_diastole_RR"])
 assert len(PSD_FEATURE_NAMES) == native.CYCLE_PSD_FEATURES
+MOMENT_FEATURE_NAMES = tuple(["skew_" + s for s in ("RR",) + _STATES] + ["kurtosis_" + s for s in ("RR",) + _STATES])
+assert len(MOMENT_FEATURE_NAMES) == native.CYCLE_MOMENT_FEATURES
 
 
 def _frames_on_device(frames, batch: int, device) -> torch.Tensor:
@@ -107,14 +110,33 @@ def cycle_psd_features(data: torch.Tensor, frames, channel: int = 4, fs: int = 1
     return out
 
 
+def cycle_moment_features(data: torch.Tensor, frames, channel: int = 4, out: torch.Tensor = None,
+                          err_flag: torch.Tensor = None) -> torch.Tensor:
+    """``(B, 10)`` float32: ``scipy.stats.skew`` and ``scipy.stats.kurtosis`` of the whole beat and the four states of
+    ``data[:, channel]`` (layout: :data:`MOMENT_FEATURE_NAMES`; classical.py:893-905).  There is no CPU path."""
+    if not isinstance(data, torch.Tensor) or not data.is_cuda:
+        raise RuntimeError("cycle_moment_features: data must be a CUDA tensor (there is no CPU fallback)")
+    if data.dim() != 3 or data.dtype != torch.float32:
+        raise ValueError("cycle_moment_features: data must be (B, C, L) float32")
+    if not 0 <= channel < data.shape[1]:
+        raise ValueError(f"channel {channel} outside the {data.shape[1]} channels of the batch")
+    data = data if data.is_contiguous() else data.contiguous()
+    if out is None:
+        out = torch.empty((data.shape[0], native.CYCLE_MOMENT_FEATURES), dtype=torch.float32, device=data.device)
+    native.cycle_moment_features(data, _frames_on_device(frames, data.shape[0], data.device), channel, out, err_flag)
+    return out
+
+
 def classical_space_features(data: torch.Tensor, frames, channel: int = 4, fs: int = 1000, psd: bool = True):
-    """Duration, amplitude, envelope and (``psd``) PSD blocks for a whole batch: ``(names, values)`` with ``values`` a
-    (B, 14 + 36 [+ 80]) float64 device tensor in the reference's order of computation (durations first)."""
+    """Duration, amplitude, envelope and (``psd``) PSD and moments blocks for a whole batch: ``(names, values)`` with
+    ``values`` a (B, 14 + 36 [+ 80 + 10]) float64 device tensor in the reference's order of computation (durations first)."""
     from . import segmentation
     frames_dev = _frames_on_device(frames, data.shape[0], data.device)
     dur = segmentation.duration_features(frames_dev, fs)
     feats = cycle_features(data, frames_dev, channel)
     names, cols = DURATION_NAMES + FEATURE_NAMES, [dur, feats.to(torch.float64)]
     if psd:
-        names, cols = names + PSD_FEATURE_NAMES, cols + [cycle_psd_features(data, frames_dev, channel, 1000).to(torch.float64)]
+        names = names + PSD_FEATURE_NAMES + MOMENT_FEATURE_NAMES
+        cols = cols + [cycle_psd_features(data, frames_dev, channel, 1000).to(torch.float64),
+                       cycle_moment_features(data, frames_dev, channel).to(torch.float64)]
     return names, torch.cat(cols, dim=1)

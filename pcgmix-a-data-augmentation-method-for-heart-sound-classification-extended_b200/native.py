@@ -25,6 +25,7 @@ ERR_ZERO_DIVISION = 16
 ERR_EMPTY_STATE = 32
 CYCLE_FEATURES = 36
 CYCLE_PSD_FEATURES = 80
+CYCLE_MOMENT_FEATURES = 10
 MAX_KNOT = 30
 
 _c_i32 = ctypes.c_int32
@@ -55,6 +56,7 @@ SIGNATURES = {
     "pcgmix_duration_features": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_cycle_features": [_ptr, _ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_cycle_psd_features": [_ptr, _ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
+    "pcgmix_cycle_moment_features": [_ptr, _ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_mix1d_resident": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr, _c_f32, _c_f32,
                               _ptr, _ptr, _ptr, _c_i32, _ptr, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_copy_small": [_ptr, _ptr, ctypes.c_int64, _ptr],
@@ -573,6 +575,25 @@ def duration_features(frames, n, fs, features, err_flag=None):
             _stream_handle(dev))
     _check(rc, "pcgmix_duration_features")
     launch_count += 1 if n > 0 else 0
+
+
+def cycle_moment_features(x, frames, channel: int, features, err_flag=None):
+    """Skewness / kurtosis block of ``feature_vector_seg`` for ``x[:, channel]``; see ``pcgmix_cycle_moment_features``."""
+    global launch_count
+    if x.dim() != 3:
+        raise ValueError("x must be (B, C, L)")
+    B, C, L = x.shape
+    if tuple(features.shape) != (B, CYCLE_MOMENT_FEATURES):
+        raise ValueError(f"features must be (B, {CYCLE_MOMENT_FEATURES})")
+    _check_rows(B, frames=frames)
+    dev = _same_device(x, frames, features, err_flag)
+    fptr, fstride = _frames_ptr(frames)
+    with _on_device(dev):
+        rc = load().pcgmix_cycle_moment_features(_dev_ptr(x, torch.float32, "x"), fptr, fstride, B, C, L, int(channel),
+                                                 _dev_ptr(features, torch.float32, "features"),
+                                                 _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
+    _check(rc, "pcgmix_cycle_moment_features")
+    launch_count += 1 if B > 0 else 0
 
 
 def cycle_psd_features(x, frames, channel: int, fs: int, features, err_flag=None):

@@ -94,10 +94,11 @@ def test_features_of_an_augmented_batch_match_the_oracle():
     ohe = torch.nn.functional.one_hot(torch.from_numpy(labels), 2).to(dev)
     out, _, _, _ = augmentations.augment(Args, torch.from_numpy(x).to(dev), ohe, torch.from_numpy(frames), ["a"] * b, Step, None, dev, None)
     names, table = features.classical_space_features(out, torch.from_numpy(frames), channel=4)
-    assert len(names) == 130 and table.shape == (b, 130) and table.dtype == torch.float64
+    assert len(names) == 140 and table.shape == (b, 140) and table.dtype == torch.float64
     want = forc.batch_features(out.cpu().numpy(), frames, 4)
     _check_block(table[:, 14:50].cpu().numpy().astype(np.float32), want, 3)
-    _check_psd(table[:, 50:].cpu().numpy(), forc.batch_psd_features(out.cpu().numpy(), frames, 4))
+    _check_psd(table[:, 50:130].cpu().numpy(), forc.batch_psd_features(out.cpu().numpy(), frames, 4))
+    _check_moments(table[:, 130:].cpu().numpy(), forc.batch_moment_features(out.cpu().numpy(), frames, 4))
     names50, table50 = features.classical_space_features(out, torch.from_numpy(frames), channel=4, psd=False)
     assert len(names50) == 50 and torch.equal(table50, table[:, :50])
     assert table[0, 0].item() == int(frames[0, 4] * 1000 / 1000)          # duration_RR in ms
@@ -220,3 +221,62 @@ def test_psd_other_sampling_rate_moves_the_bands():
         warnings.simplefilter("ignore")
         want = np.stack([forc.cycle_psd_features(x[i, 0], frames[i], 2000) for i in range(4)])
     _check_psd(out, want)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Moments block (classical.py:893-905): scipy.stats.skew / kurtosis of the beat and the four states, float32 like
+# SciPy's for float32 rows.  2e-5 relative + 2e-6 absolute: a skewness near zero is a difference of large terms in
+# both implementations.
+
+def _check_moments(got, want):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    assert got.shape == want.shape and got.shape[1] == 10
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert (np.abs(got[ok] - want[ok]) <= REL * np.abs(want[ok]) + 2e-6).all(), float(np.abs(got[ok] - want[ok]).max())
+
+
+def test_moment_oracle_matches_reference_statements_bitwise(golden):
+    import warnings
+    g, m = golden("cycle_psd_features"), golden("cycle_moment_features")
+    assert m["features"].shape == (64, 10)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = forc.batch_moment_features(g["data"][:, None, :], g["frames"], 0)
+    assert np.array_equal(got, m["features"])
+
+
+def test_moment_feature_names_are_the_reference_variable_names(golden):
+    from pcgmix_b200 import features
+    assert [str(n) for n in golden("cycle_moment_features")["names"]] == list(features.MOMENT_FEATURE_NAMES)
+
+
+@pytest.mark.gpu
+def test_moment_kernel_vs_reference_fixture(golden):
+    from pcgmix_b200 import features
+    g, m = golden("cycle_psd_features"), golden("cycle_moment_features")
+    rng = np.random.default_rng(4)
+    batch = rng.standard_normal((64, 5, 2500)).astype(np.float32)
+    batch[:, 4] = g["data"]
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = features.cycle_moment_features(torch.from_numpy(batch).cuda(), torch.from_numpy(g["frames"]), channel=4, err_flag=err)
+    assert out.shape == (64, 10) and out.dtype == torch.float32 and int(err.item()) == 0
+    _check_moments(out.cpu().numpy(), m["features"])
+
+
+@pytest.mark.gpu
+def test_moment_kernel_flat_and_empty_segments():
+    import warnings
+    from pcgmix_b200 import features, native
+    x = torch.randn(3, 1, 400, device="cuda")
+    x[1, 0, 100:200] = 0.25                                   # a constant systole: no variance -> NaN like SciPy
+    frames = torch.tensor([[0, 100, 200, 300, 390], [0, 100, 200, 300, 390], [0, 100, 100, 300, 390]])     # third: empty systole
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = features.cycle_moment_features(x, frames, channel=0, err_flag=err).cpu().numpy()
+    assert int(err.item()) == native.ERR_EMPTY_STATE
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = np.stack([forc.cycle_moment_features(x[i, 0].cpu().numpy(), frames[i].numpy()) for i in range(2)])
+    _check_moments(out[:2], want)
+    assert np.isnan(out[1, 2]) and np.isnan(out[1, 7])        # skew / kurtosis of the constant systole
+    assert np.isnan(out[2, 2]) and np.isnan(out[2, 7]) and np.isfinite(out[2, [0, 1, 3, 4]]).all()
