@@ -175,7 +175,7 @@ def resident_section(args, dev):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=200)
-    ap.add_argument("--only", default="", choices=["", "resident"])
+    ap.add_argument("--only", default="", choices=["", "resident", "first_block"])
     ap.add_argument("--stages", type=int, default=0)
     ap.add_argument("--ctas-per-sm", type=int, default=0)
     ap.add_argument("--consumer-threads", type=int, default=0)
@@ -210,6 +210,8 @@ def run(args, dev):
     cpu_legs = getattr(args, "cpu_legs", True)
     if args.only == "resident":
         return resident_section(args, dev)
+    if args.only == "first_block":
+        return first_block_section(args, dev, cpu_legs)
     rng = np.random.default_rng(synth.BENCH_SEED)
 
     # ---------------- cfg1 ----------------
@@ -329,6 +331,7 @@ def run(args, dev):
          4.0 * F5 * (2.0 * T5 * B5 + synth.mixed_samples(frames5, mix5)))
     resident_section(args, dev)
     features_section(args, dev, cpu_legs)
+    first_block_section(args, dev, cpu_legs)
 
 
 def features_section(args, dev, cpu_legs):
@@ -352,6 +355,47 @@ def features_section(args, dev, cpu_legs):
         emit("features/CPU port (NumPy / SciPy calls of the reference, one core) on a 64-cycle sample: amplitude + envelope", 64,
              t_env * 1e3, t_env * 1e3)
         emit("features/CPU port on a 64-cycle sample: Welch-PSD block", 64, t_psd * 1e3, t_psd * 1e3)
+
+
+def first_block_section(args, dev, cpu_legs):
+    """The model side (train_model.py:536 -> models.py:538): conv1 = Conv1d(4, 64, 3, padding=1) + BatchNorm1d + ReLU of the
+    reference's ResNet9-1D on an augmented batch.  Bound by writing the 16x larger output; bytes = input read (twice in
+    training mode: patch moments, then the pass that writes) + output written."""
+    from pcgmix_b200 import first_block
+    rng = np.random.default_rng(synth.BENCH_SEED + 6)
+    C, L, F = 4, 2500, 64
+    torch.manual_seed(6)
+    block = torch.nn.Sequential(torch.nn.Conv1d(C, F, 3, padding=1), torch.nn.BatchNorm1d(F), torch.nn.ReLU(inplace=True)).to(dev)
+    frames = synth.cycle_frames(rng, 512, limit=L)
+    base = torch.from_numpy(synth.cycle_signals(rng, frames, (C,), L)).to(dev)
+    saved_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                   # the library leg beside ours must be a float32 one too
+    for B in (4096, 64):
+        data = base.repeat(B // 512, 1, 1).contiguous() if B >= 512 else base[:B].contiguous()
+        out = torch.empty((B, F, L), dtype=torch.float32, device=dev)
+        for training in (True, False):
+            block.train(training)
+            ms, mn = timed(lambda i: first_block.first_conv_block(block, data, out=out), 20, warm=3)
+            emit("first block/conv1 + BatchNorm + ReLU (%s statistics) of %d cycles x 4 x 2500 -> 64 x 2500" %
+                 ("batch" if training else "running", B), B, ms, mn, 4.0 * B * L * (C * (2 if training else 1) + F))
+            with torch.no_grad():
+                ms, mn = timed(lambda i: block(data), 10, warm=3)
+            emit("first block/the same modules run by torch (cuDNN, float32; library, beside ours), %s statistics, %d cycles" %
+                 ("batch" if training else "running", B), B, ms, mn, 4.0 * B * L * (C * (2 if training else 1) + F))
+        del out
+    torch.backends.cudnn.allow_tf32 = saved_tf32
+    if cpu_legs:
+        import time
+        cpu_block = torch.nn.Sequential(torch.nn.Conv1d(C, F, 3, padding=1), torch.nn.BatchNorm1d(F), torch.nn.ReLU(inplace=True)).train()
+        sample = base[:64].cpu()
+        with torch.no_grad():
+            cpu_block(sample)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                cpu_block(sample)
+            dt = (time.perf_counter() - t0) / 5
+        emit("first block/CPU: the reference's modules (torch, %d threads) on a 64-cycle batch, batch statistics" % torch.get_num_threads(),
+             64, dt * 1e3, dt * 1e3)
 
 
 if __name__ == "__main__":

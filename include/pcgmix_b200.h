@@ -61,6 +61,7 @@ extern "C" {
 
 #define PCGMIX_CYCLE_FEATURES 36     /* floats per cycle written by pcgmix_cycle_features       */
 #define PCGMIX_CYCLE_PSD_FEATURES 80 /* floats per cycle written by pcgmix_cycle_psd_features   */
+#define PCGMIX_MAX_FIRST_BLOCK_FILTERS 512 /* output channels pcgmix_first_conv_block accepts (records live in shared memory) */
 #define PCGMIX_CYCLE_MOMENT_FEATURES 10 /* floats per cycle written by pcgmix_cycle_moment_features */
 
 #define PCGMIX_MAX_KNOT 30           /* largest `knot` of durmixmagwarp(sigma,knot) supported */
@@ -310,6 +311,30 @@ int pcgmix_cycle_psd_features(const float* x, const int32_t* frames, int32_t fra
 int pcgmix_cycle_moment_features(const float* x, const int32_t* frames, int32_t frame_stride, int32_t B, int32_t C,
                                  int32_t L, int32_t channel, float* features, int32_t* err_flag,
                                  pcgmix_stream_t stream);
+
+/*
+ * Forward pass of the first block of the reference's ResNet9-1D on a batch of (augmented) cycles: nn.Conv1d(C, F,
+ * kernel_size=3, padding=1) + nn.BatchNorm1d(F) + nn.ReLU — models.py:468-473 (conv_block), instantiated as conv1 at
+ * models.py:523 and applied to augment()'s output at models.py:538 / train_model.py:536.  SURVEY 8(f)4.
+ *   x [B][C][L] fp32 (C = 1..4), weight [F][C][3], bias / gamma / beta [F] or NULL (0 / 1 / 0), out [B][F][L] fp32,
+ *   disjoint from x.  F <= PCGMIX_MAX_FIRST_BLOCK_FILTERS.
+ *   batch_stats = 1 (a module in training mode, or one without running statistics): normalises with the mean and
+ *     biased variance of the convolution's output over (B, L) — obtained from second moments of the INPUT patches, so
+ *     the output is written exactly once — and, when running_mean / running_var are given, updates them in place as
+ *     torch does: running = (1 - momentum) * running + momentum * batch (variance unbiased, n / (n - 1)).
+ *   batch_stats = 0 (evaluation mode): normalises with running_mean / running_var (required), which are not changed.
+ *   save_mean / save_invstd [F] or NULL: the statistics used (what torch's batch_norm saves for its backward).
+ *   workspace: pcgmix_first_conv_block_workspace(C, F) bytes of device memory, 16-byte aligned, private to the call
+ *     until the stream has passed it.
+ * Forward only (no gradient kernels).  float32 FMAs; agrees with torch's float32 modules to rounding (tests: 2e-5
+ * relative + 2e-5 absolute on the output, 1e-5 relative on the statistics).  NaN propagates like torch's ReLU.
+ * Enqueues at most one memset and three kernels on `stream`; no allocation, no synchronisation.
+ */
+long long pcgmix_first_conv_block_workspace(int32_t C, int32_t F);   /* bytes; -1 for unsupported sizes */
+int pcgmix_first_conv_block(const float* x, const float* weight, const float* bias, const float* gamma,
+                            const float* beta, float* running_mean, float* running_var, float* out, void* workspace,
+                            int32_t B, int32_t C, int32_t L, int32_t F, int32_t batch_stats, double eps,
+                            double momentum, float* save_mean, float* save_invstd, pcgmix_stream_t stream);
 
 /* 14 fp64 features per cycle from frames [n][5] int32 (stride `frame_stride` int32 between rows). */
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,

@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB_PATH = os.path.join(CSRC, "libpcgmix_b200.so")
 OBJ_DIR = os.path.join(CSRC, "build")                      # intermediate objects (git- and gpurun-ignored)
-SOURCES = ("mix_kernels.cu", "mix_pipeline.cu", "mix_resident.cu", "segment_kernels.cu", "feature_kernels.cu", "psd_kernels.cu", "capi.cu", "host_draws.cpp")
+SOURCES = ("mix_kernels.cu", "mix_pipeline.cu", "mix_resident.cu", "segment_kernels.cu", "feature_kernels.cu", "psd_kernels.cu", "first_block_kernels.cu", "capi.cu", "host_draws.cpp")
 NVCC_FLAGS = ("-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC",
               # host code replays NumPy's / CPython's generators bit for bit: no FMA contraction there either

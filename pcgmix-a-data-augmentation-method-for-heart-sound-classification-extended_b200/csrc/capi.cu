@@ -455,6 +455,41 @@ int pcgmix_cycle_moment_features(const float* x, const int32_t* frames, int32_t 
     return e == cudaSuccess ? 0 : fail_cuda("pcgmix_cycle_moment_features", e);
 }
 
+long long pcgmix_first_conv_block_workspace(int32_t C, int32_t F) {
+    if (C < 1 || C > 4 || F < 1 || F > PCGMIX_MAX_FIRST_BLOCK_FILTERS) return -1;
+    return static_cast<long long>(pcgmix::first_conv_block_workspace_bytes(C, F));
+}
+
+int pcgmix_first_conv_block(const float* x, const float* weight, const float* bias, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, float* out, void* workspace, int32_t B, int32_t C,
+                            int32_t L, int32_t F, int32_t batch_stats, double eps, double momentum, float* save_mean,
+                            float* save_invstd, pcgmix_stream_t stream) {
+    if (B < 0 || L <= 0 || F <= 0) return fail("bad size argument");
+    if (C < 1 || C > 4) return fail("the first block takes 1 to 4 input channels");
+    if (F > PCGMIX_MAX_FIRST_BLOCK_FILTERS) return fail("too many filters (PCGMIX_MAX_FIRST_BLOCK_FILTERS)");
+    if (!mul_fits_int32(B, L) || !mul_fits_int32(static_cast<long long>(B) * ((L + 3) / 4), 1)) return fail("B*L must be below 2^31");
+    if (!(eps >= 0.0) || !(momentum >= 0.0 && momentum <= 1.0)) return fail("eps must be >= 0 and momentum in [0, 1]");
+    if (B > 0 && (x == nullptr || weight == nullptr || out == nullptr || workspace == nullptr)) return fail("null pointer argument");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15u) != 0) return fail("workspace must be 16-byte aligned");
+    if (batch_stats == 0 && (running_mean == nullptr || running_var == nullptr))
+        return fail("without batch statistics the running statistics are needed");
+    if (batch_stats != 0 && static_cast<long long>(B) * L < 2 && B > 0)
+        return fail("batch statistics need more than one value per filter");     // torch raises here too
+    {
+        const uintptr_t xb = reinterpret_cast<uintptr_t>(x), ob = reinterpret_cast<uintptr_t>(out);
+        const uintptr_t xn = static_cast<uintptr_t>(B) * C * L * sizeof(float), on = static_cast<uintptr_t>(B) * F * L * sizeof(float);
+        if (B > 0 && xb < ob + on && ob < xb + xn) return fail("x and out must not overlap");
+    }
+    forget_stream(static_cast<cudaStream_t>(stream));
+    pcgmix::FirstBlockArgs p;
+    p.x = x; p.weight = weight; p.bias = bias; p.gamma = gamma; p.beta = beta;
+    p.running_mean = running_mean; p.running_var = running_var; p.out = out; p.workspace = workspace;
+    p.save_mean = save_mean; p.save_invstd = save_invstd; p.eps = eps; p.momentum = momentum;
+    p.B = B; p.C = C; p.L = L; p.F = F; p.batch_stats = batch_stats != 0 ? 1 : 0;
+    const cudaError_t e = pcgmix::launch_first_conv_block(p, static_cast<cudaStream_t>(stream));
+    return e == cudaSuccess ? 0 : fail_cuda("pcgmix_first_conv_block", e);
+}
+
 int pcgmix_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs, double* features,
                              int32_t* err_flag, pcgmix_stream_t stream) {
     if (n < 0 || fs <= 0 || frame_stride < 5) return fail("bad size argument");

@@ -146,4 +146,25 @@ cudaError_t launch_cycle_moment_features(const float* x, const int32_t* frames, 
 cudaError_t launch_duration_features(const int32_t* frames, int32_t frame_stride, int32_t n, int32_t fs,
                                      double* features, int32_t* err, cudaStream_t stream);
 
+// first_block_kernels.cu — Conv1d(C -> F, k=3, pad=1) + BatchNorm1d + ReLU forward of the reference's first model block
+struct FirstBlockArgs {
+    const float* x;            // [B][C][L]
+    const float* weight;       // [F][C][3]
+    const float* bias;         // [F] or nullptr
+    const float* gamma;        // [F] or nullptr
+    const float* beta;         // [F] or nullptr
+    float* running_mean;       // [F] or nullptr; updated in place when batch statistics are used
+    float* running_var;        // [F] or nullptr
+    float* out;                // [B][F][L]
+    void* workspace;           // first_conv_block_workspace_bytes(C, F), 16-byte aligned
+    float* save_mean;          // [F] or nullptr: the mean / inverse standard deviation the block normalised with
+    float* save_invstd;
+    double eps;
+    double momentum;
+    int32_t B, C, L, F;
+    int32_t batch_stats;       // 1: statistics of this batch (training mode), 0: the running statistics
+};
+size_t first_conv_block_workspace_bytes(int32_t C, int32_t F);
+cudaError_t launch_first_conv_block(const FirstBlockArgs& p, cudaStream_t stream);
+
 }  // namespace pcgmix

@@ -27,6 +27,7 @@ CYCLE_FEATURES = 36
 CYCLE_PSD_FEATURES = 80
 CYCLE_MOMENT_FEATURES = 10
 MAX_KNOT = 30
+MAX_FIRST_BLOCK_FILTERS = 512
 
 _c_i32 = ctypes.c_int32
 _c_f32 = ctypes.c_float
@@ -57,6 +58,9 @@ SIGNATURES = {
     "pcgmix_cycle_features": [_ptr, _ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_cycle_psd_features": [_ptr, _ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_cycle_moment_features": [_ptr, _ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32, _ptr, _ptr, _ptr],
+    "pcgmix_first_conv_block_workspace": [_c_i32, _c_i32],
+    "pcgmix_first_conv_block": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _c_i32, _c_i32, _c_i32, _c_i32, _c_i32,
+                                ctypes.c_double, ctypes.c_double, _ptr, _ptr, _ptr],
     "pcgmix_mix1d_resident": [_ptr, _c_i32, _c_i32, _c_i32, _ptr, _c_i32, _ptr, _ptr, _ptr, _c_f32, _c_f32,
                               _ptr, _ptr, _ptr, _c_i32, _ptr, _c_i32, _c_i32, _ptr, _ptr, _ptr],
     "pcgmix_copy_small": [_ptr, _ptr, ctypes.c_int64, _ptr],
@@ -115,7 +119,8 @@ def load(build_if_missing: bool = True):
             fn = getattr(lib, name)
             fn.argtypes = argtypes
             fn.restype = (ctypes.c_char_p if name == "pcgmix_last_error" else
-                          ctypes.c_longlong if name == "pcgmix_overlap_launches" else ctypes.c_int)
+                          ctypes.c_longlong if name in ("pcgmix_overlap_launches", "pcgmix_first_conv_block_workspace")
+                          else ctypes.c_int)
         _lib = lib
     return _lib
 
@@ -594,6 +599,46 @@ def cycle_moment_features(x, frames, channel: int, features, err_flag=None):
                                                  _dev_ptr(err_flag, torch.int32, "err_flag", True), _stream_handle(dev))
     _check(rc, "pcgmix_cycle_moment_features")
     launch_count += 1 if B > 0 else 0
+
+
+def first_conv_block_workspace(C: int, F: int) -> int:
+    """Bytes of device workspace ``first_conv_block`` needs for ``C`` input channels and ``F`` filters."""
+    n = int(load().pcgmix_first_conv_block_workspace(int(C), int(F)))
+    if n < 0:
+        raise ValueError(f"first_conv_block: unsupported size (C={C} must be 1..4, F={F} at most {MAX_FIRST_BLOCK_FILTERS})")
+    return n
+
+
+def first_conv_block(x, weight, bias, gamma, beta, running_mean, running_var, out, workspace, batch_stats: bool,
+                     eps: float, momentum: float, save_mean=None, save_invstd=None):
+    """Conv1d(C, F, 3, padding=1) + BatchNorm1d + ReLU forward; see ``pcgmix_first_conv_block`` in the header."""
+    global launch_count
+    if x.dim() != 3 or weight.dim() != 3:
+        raise ValueError("x must be (B, C, L) and weight (F, C, 3)")
+    B, C, L = x.shape
+    F = weight.shape[0]
+    if tuple(weight.shape) != (F, C, 3):
+        raise ValueError(f"weight must be (F, {C}, 3), got {tuple(weight.shape)}")
+    if tuple(out.shape) != (B, F, L):
+        raise ValueError(f"out must be ({B}, {F}, {L}), got {tuple(out.shape)}")
+    for name, t in (("bias", bias), ("gamma", gamma), ("beta", beta), ("running_mean", running_mean),
+                    ("running_var", running_var), ("save_mean", save_mean), ("save_invstd", save_invstd)):
+        if t is not None and tuple(t.shape) != (F,):
+            raise ValueError(f"{name} must have {F} entries, got {tuple(t.shape)}")
+    if workspace.dtype != torch.uint8 or workspace.numel() < first_conv_block_workspace(C, F):
+        raise ValueError("workspace must be a uint8 tensor of first_conv_block_workspace(C, F) bytes")
+    dev = _same_device(x, weight, bias, gamma, beta, running_mean, running_var, out, workspace, save_mean, save_invstd)
+    f32 = torch.float32
+    with _on_device(dev):
+        rc = load().pcgmix_first_conv_block(
+            _dev_ptr(x, f32, "x"), _dev_ptr(weight, f32, "weight"), _dev_ptr(bias, f32, "bias", True),
+            _dev_ptr(gamma, f32, "gamma", True), _dev_ptr(beta, f32, "beta", True),
+            _dev_ptr(running_mean, f32, "running_mean", True), _dev_ptr(running_var, f32, "running_var", True),
+            _dev_ptr(out, f32, "out"), _dev_ptr(workspace, torch.uint8, "workspace"), B, C, L, F, 1 if batch_stats else 0,
+            float(eps), float(momentum), _dev_ptr(save_mean, f32, "save_mean", True),
+            _dev_ptr(save_invstd, f32, "save_invstd", True), _stream_handle(dev))
+    _check(rc, "pcgmix_first_conv_block")
+    launch_count += (3 if batch_stats else 2) if B > 0 else 0
 
 
 def cycle_psd_features(x, frames, channel: int, fs: int, features, err_flag=None):
