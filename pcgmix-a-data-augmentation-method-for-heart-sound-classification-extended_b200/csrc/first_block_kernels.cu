@@ -40,6 +40,7 @@ namespace pcgmix {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kMomentThreads = 128;     // patch_moments_kernel
 
 __host__ __device__ constexpr int patch_len(int C) { return 3 * C; }
 __host__ __device__ constexpr int moment_count(int C) { return patch_len(C) + patch_len(C) * (patch_len(C) + 1) / 2; }
@@ -58,72 +59,135 @@ __device__ __forceinline__ float relu_nan(float v) {    // torch's ReLU keeps Na
     return r;
 }
 
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));     // two IEEE float32 FMAs, one issue slot
+    return d;
+}
+
 // moments[i] = sum v_i, moments[P + tri(i, j)] = sum v_i v_j (i <= j), over all (b, l).  `moments` zeroed by the caller.
-template <int C>
-__global__ void __launch_bounds__(kThreads) patch_moments_kernel(const float* __restrict__ x, uint32_t total, uint32_t L,
-                                                                  double* __restrict__ moments) {
+// Persistent: the grid is the number of CTAs the GPU holds at once.  A thread takes four adjacent positions at a time
+// (one 128-bit load and two border samples per channel, like apply_kernel; the next window is fetched before the
+// current one's arithmetic), so a batch of 3C loads feeds 4 x 48 packed FMAs.  Row a of the product triangle is
+// accumulated as packed pairs (v[a], v[a]) * (v[2k], v[2k+1]), k >= a / 2 — 42 FFMA2 instead of 78 FFMA at C = 4 (one
+// product per odd row is computed twice and dropped).  A thread sums its own positions in float32 (a hundred-odd
+// terms), a warp's 32 partial sums are added by a float32 shuffle tree, everything above that is float64.
+template <int C, bool VEC>
+__global__ void __launch_bounds__(kMomentThreads, 2) patch_moments_kernel(const float* __restrict__ x, uint32_t total_quads,
+                                                                         uint32_t quads_per_row, uint32_t L,
+                                                                         double* __restrict__ moments) {
     constexpr int P = patch_len(C);
+    constexpr int HP = (P + 1) / 2;                         // packed pairs per patch (the last one padded with 0 when P is odd)
     constexpr int NM = moment_count(C);
     __shared__ double s_acc[NM];
-    for (int i = threadIdx.x; i < NM; i += kThreads) s_acc[i] = 0.0;
+    for (int i = threadIdx.x; i < NM; i += kMomentThreads) s_acc[i] = 0.0;
     __syncthreads();
 
-    float s1[P];
-    float s2[P * (P + 1) / 2];
+    unsigned long long s1[HP];
+    unsigned long long s2[P][HP];                           // row a uses k >= a / 2 only; the rest is never touched
 #pragma unroll
-    for (int i = 0; i < P; ++i) s1[i] = 0.0f;
+    for (int k = 0; k < HP; ++k) s1[k] = 0ull;
 #pragma unroll
-    for (int i = 0; i < P * (P + 1) / 2; ++i) s2[i] = 0.0f;
+    for (int a = 0; a < P; ++a)
+#pragma unroll
+        for (int k = 0; k < HP; ++k) s2[a][k] = 0ull;
+    const unsigned long long ones = pack2(1.0f, 1.0f);
 
-    // the next position's patch is fetched before the current one's 3C + 3C(3C+1)/2 FMAs are issued
-    auto fetch = [&](uint32_t i, float (&v)[P]) {
-        const uint32_t b = i / L;
-        const uint32_t l = i - b * L;
+    // samples l0-1 .. l0+4 of every channel, zero outside the row
+    auto fetch = [&](uint32_t t, float (&w)[C][6], uint32_t& l0) {
+        const uint32_t b = t / quads_per_row;
+        l0 = (t - b * quads_per_row) * 4u;
         const float* row = x + static_cast<size_t>(b) * C * L;
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const float* r = row + static_cast<size_t>(c) * L;
-            v[3 * c + 0] = l > 0 ? __ldg(r + l - 1) : 0.0f;
-            v[3 * c + 1] = __ldg(r + l);
-            v[3 * c + 2] = l + 1 < L ? __ldg(r + l + 1) : 0.0f;
+            if (VEC) {
+                const float4 m = __ldg(reinterpret_cast<const float4*>(r + l0));
+                w[c][1] = m.x; w[c][2] = m.y; w[c][3] = m.z; w[c][4] = m.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) w[c][1 + j] = l0 + j < L ? __ldg(r + l0 + j) : 0.0f;
+            }
+            w[c][0] = l0 > 0 ? __ldg(r + l0 - 1) : 0.0f;
+            w[c][5] = l0 + 4 < L ? __ldg(r + l0 + 4) : 0.0f;
         }
     };
-    const uint32_t step = gridDim.x * kThreads;
-    uint32_t i = blockIdx.x * kThreads + threadIdx.x;
-    float nv[P];
+    const uint32_t step = gridDim.x * kMomentThreads;
+    uint32_t t = blockIdx.x * kMomentThreads + threadIdx.x;
+    float nw[C][6];
+    uint32_t nl0 = 0;
 #pragma unroll
-    for (int a = 0; a < P; ++a) nv[a] = 0.0f;
-    if (i < total) fetch(i, nv);
-    while (i < total) {
-        float v[P];
+    for (int c = 0; c < C; ++c)
 #pragma unroll
-        for (int a = 0; a < P; ++a) v[a] = nv[a];
-        const uint32_t ni = i + step;
-        if (ni < total && ni > i) fetch(ni, nv);
-        int t = 0;
+        for (int j = 0; j < 6; ++j) nw[c][j] = 0.0f;
+    if (t < total_quads) fetch(t, nw, nl0);
+    while (t < total_quads) {
+        float w[C][6];
+        unsigned long long wd[C][6];                        // (x, x)
 #pragma unroll
-        for (int a = 0; a < P; ++a) {
-            s1[a] += v[a];
+        for (int c = 0; c < C; ++c)
 #pragma unroll
-            for (int q = a; q < P; ++q, ++t) s2[t] = fmaf(v[a], v[q], s2[t]);
+            for (int j = 0; j < 6; ++j) { w[c][j] = nw[c][j]; wd[c][j] = pack2(nw[c][j], nw[c][j]); }
+        const uint32_t l0 = nl0;
+        const uint32_t nt = t + step;
+        if (nt < total_quads && nt > t) fetch(nt, nw, nl0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (!VEC && l0 + j >= L) break;                 // ragged last quad of a row: no such position
+            unsigned long long vp[HP];
+#pragma unroll
+            for (int k = 0; k < HP; ++k) {
+                const int i0 = 2 * k, i1 = 2 * k + 1;
+                const float lo = w[i0 / 3][j + i0 % 3];
+                const float hi = i1 < P ? w[i1 / 3][j + i1 % 3] : 0.0f;
+                vp[k] = pack2(lo, hi);
+            }
+#pragma unroll
+            for (int k = 0; k < HP; ++k) s1[k] = fma2(vp[k], ones, s1[k]);
+#pragma unroll
+            for (int a = 0; a < P; ++a) {
+                const unsigned long long va = wd[a / 3][j + a % 3];
+#pragma unroll
+                for (int k = a / 2; k < HP; ++k) s2[a][k] = fma2(va, vp[k], s2[a][k]);
+            }
         }
-        if (ni <= i) break;                                 // 32-bit wrap-around guard (total close to 2^32)
-        i = ni;
+        if (nt <= t) break;                                 // 32-bit wrap-around guard
+        t = nt;
     }
 
     const int lane = threadIdx.x & 31;
+    auto warp_add = [&](float v, int slot) {
 #pragma unroll
-    for (int i = 0; i < P; ++i) {
-        const double r = warp_sum_f64(static_cast<double>(s1[i]));
-        if (lane == 0) atomicAdd(&s_acc[i], r);
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+        if (lane == 0) atomicAdd(&s_acc[slot], static_cast<double>(v));
+    };
+#pragma unroll
+    for (int k = 0; k < HP; ++k) {
+        float lo, hi;
+        unpack2(s1[k], lo, hi);
+        warp_add(lo, 2 * k);
+        if (2 * k + 1 < P) warp_add(hi, 2 * k + 1);
     }
+    int idx = 0;
 #pragma unroll
-    for (int i = 0; i < P * (P + 1) / 2; ++i) {
-        const double r = warp_sum_f64(static_cast<double>(s2[i]));
-        if (lane == 0) atomicAdd(&s_acc[P + i], r);
+    for (int a = 0; a < P; ++a) {
+#pragma unroll
+        for (int q = a; q < P; ++q, ++idx) {
+            float lo, hi;
+            unpack2(s2[a][q / 2], lo, hi);
+            warp_add((q & 1) ? hi : lo, P + idx);
+        }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < NM; i += kThreads) atomicAdd(&moments[i], s_acc[i]);
+    for (int i2 = threadIdx.x; i2 < NM; i2 += kMomentThreads) atomicAdd(&moments[i2], s_acc[i2]);
 }
 
 struct FoldArgs {
@@ -144,12 +208,29 @@ struct FoldArgs {
     int C;
 };
 
-// One thread per filter, float64.  Writes the folded record of every filter; with batch statistics also the
-// running-statistics update (running = (1 - m) running + m batch, variance unbiased) torch performs in training mode.
-__global__ void fold_kernel(FoldArgs a) {
+// One CTA.  Means and (doubled off-diagonal) covariances of the patch first, one thread per entry, then one thread per
+// filter, float64.  Writes the folded record of every filter; with batch statistics also the running-statistics update
+// (running = (1 - m) running + m batch, variance unbiased) torch performs in training mode.
+constexpr int kFoldThreads = 128;
+__global__ void __launch_bounds__(kFoldThreads) fold_kernel(FoldArgs a) {
+    constexpr int kMaxP = patch_len(4);
+    __shared__ double s_mu[kMaxP];
+    __shared__ double s_cov[kMaxP * (kMaxP + 1) / 2];
     const int P = 3 * a.C;
     const int PS = (2 * P + 2 + 3) & ~3;
-    for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < a.F; f += gridDim.x * blockDim.x) {
+    if (a.moments != nullptr) {
+        const double inv_n = 1.0 / a.n;
+        for (int i = threadIdx.x; i < P; i += kFoldThreads) s_mu[i] = a.moments[i] * inv_n;
+        __syncthreads();
+        for (int t = threadIdx.x; t < P * (P + 1) / 2; t += kFoldThreads) {
+            int i = 0, rem = t;
+            while (rem >= P - i) { rem -= P - i; ++i; }
+            const int j = i + rem;
+            s_cov[t] = (a.moments[P + t] * inv_n - s_mu[i] * s_mu[j]) * (j == i ? 1.0 : 2.0);
+        }
+        __syncthreads();
+    }
+    for (int f = threadIdx.x; f < a.F; f += kFoldThreads) {
         const float* w = a.weight + static_cast<size_t>(f) * P;
         const double bias = a.bias ? static_cast<double>(a.bias[f]) : 0.0;
         double mean, var;
@@ -157,13 +238,9 @@ __global__ void fold_kernel(FoldArgs a) {
             double m = 0.0, q = 0.0;
             int t = 0;
             for (int i = 0; i < P; ++i) {
-                const double mi = a.moments[i] / a.n;
-                m += static_cast<double>(w[i]) * mi;
-                for (int j = i; j < P; ++j, ++t) {
-                    const double cov = a.moments[P + t] / a.n - mi * (a.moments[j] / a.n);
-                    const double term = static_cast<double>(w[i]) * static_cast<double>(w[j]) * cov;
-                    q += (j == i) ? term : 2.0 * term;
-                }
+                const double wi = static_cast<double>(w[i]);
+                m += wi * s_mu[i];
+                for (int j = i; j < P; ++j, ++t) q += wi * static_cast<double>(w[j]) * s_cov[t];
             }
             mean = bias + m;
             var = q < 0.0 ? 0.0 : q;                       // rounding only; NaN stays NaN like torch's statistics
@@ -192,20 +269,6 @@ __global__ void fold_kernel(FoldArgs a) {
         if (a.save_mean != nullptr) a.save_mean[f] = static_cast<float>(mean);
         if (a.save_invstd != nullptr) a.save_invstd[f] = static_cast<float>(invstd);
     }
-}
-
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpack2(unsigned long long v, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-    unsigned long long d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));     // two IEEE float32 FMAs, one issue slot
-    return d;
 }
 
 // One thread = four adjacent output positions of one cycle, all F filters, two filters at a time: the 6-sample
@@ -308,21 +371,26 @@ template <int C>
 cudaError_t launch_for_channels(const float* x, const FoldArgs& fold_in, float* out, double* moments, int32_t B, int32_t L,
                                 int32_t F, bool batch_stats, cudaStream_t stream) {
     FoldArgs fold = fold_in;
-    const uint32_t total = static_cast<uint32_t>(B) * static_cast<uint32_t>(L);
     if (batch_stats) {
         cudaError_t e = cudaMemsetAsync(moments, 0, sizeof(double) * moment_count(C), stream);
         if (e != cudaSuccess) return e;
-        // a multiple of the SM count; a thread sums at most a few dozen float32 products before the float64 reduction
-        const uint32_t want = (total + kThreads - 1) / kThreads;
-        const uint32_t cap = static_cast<uint32_t>(sm_count_of_current_device()) * 8u;
-        patch_moments_kernel<C><<<want < cap ? want : cap, kThreads, 0, stream>>>(x, total, static_cast<uint32_t>(L), moments);
+        // persistent: as many CTAs as the GPU holds at once (a multiple of the SM count), each ends with one reduction
+        const uint32_t qpr = (static_cast<uint32_t>(L) + 3u) / 4u;
+        const uint32_t quads = static_cast<uint32_t>(B) * qpr;
+        const bool vec_in = (L % 4 == 0) && (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+        auto kernel = vec_in ? patch_moments_kernel<C, true> : patch_moments_kernel<C, false>;
+        int per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kMomentThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const uint32_t want = (quads + kMomentThreads - 1) / kMomentThreads;
+        const uint32_t cap = static_cast<uint32_t>(sm_count_of_current_device()) * static_cast<uint32_t>(per_sm);
+        kernel<<<want < cap ? want : cap, kMomentThreads, 0, stream>>>(x, quads, qpr, static_cast<uint32_t>(L), moments);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         fold.moments = moments;
     } else {
         fold.moments = nullptr;
     }
-    fold_kernel<<<(F + 127) / 128, 128, 0, stream>>>(fold);
+    fold_kernel<<<1, kFoldThreads, 0, stream>>>(fold);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
 
