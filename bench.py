@@ -25,7 +25,8 @@ Numbers on the JSON line
                  on the PCIe link (what a training loop really moves): the result consumed on the
                  device, and batches drawn from recordings that stay on the device
   configs ...... device-timed legs of the other BASELINE configurations (cfg1, cfg3, cfg4, the resident
-                 path); cfg5 ..... the DDP training step fed by the on-device augmentation
+                 path) and of the consumers of the augmented batch (classical features, the model's first
+                 block); cfg5 ..... the DDP training step fed by the on-device augmentation
   cpu_baseline . the reference's own ``augment`` (byte-compiled under oracle/_ref) or, without it, the
                  CPU oracle port, timed on this box's host cores on a bounded sample of the workload
 

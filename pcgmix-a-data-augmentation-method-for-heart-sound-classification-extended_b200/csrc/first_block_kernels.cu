@@ -278,14 +278,16 @@ __global__ void __launch_bounds__(kFoldThreads) fold_kernel(FoldArgs a) {
 template <int C, bool VEC>
 __global__ void __launch_bounds__(kThreads, 2) apply_kernel(const float* __restrict__ x, const float* __restrict__ records,
                                                              float* __restrict__ out, uint32_t total_quads, uint32_t quads_per_row,
-                                                             uint32_t L, int F) {
+                                                             uint32_t L, int F, int pairs_per_group) {
     constexpr int P = patch_len(C);
     constexpr int PS = pair_stride(C);
-    extern __shared__ float4 s_rec[];                       // [(F + 1) / 2][PS / 4]
-    const int pairs = (F + 1) >> 1;
+    extern __shared__ float4 s_rec[];                       // [pairs_per_group][PS / 4]
+    // blockIdx.y: a group of filter pairs (one group for large batches; small batches are split so that the GPU is filled)
+    const int p_begin = blockIdx.y * pairs_per_group;
+    const int p_end = min((F + 1) >> 1, p_begin + pairs_per_group);
     {
-        const float4* src = reinterpret_cast<const float4*>(records);
-        for (int i = threadIdx.x; i < pairs * (PS / 4); i += kThreads) s_rec[i] = __ldg(src + i);
+        const float4* src = reinterpret_cast<const float4*>(records) + p_begin * (PS / 4);
+        for (int i = threadIdx.x; i < (p_end - p_begin) * (PS / 4); i += kThreads) s_rec[i] = __ldg(src + i);
     }
     __syncthreads();
 
@@ -313,13 +315,13 @@ __global__ void __launch_bounds__(kThreads, 2) apply_kernel(const float* __restr
         for (int j = 0; j < 6; ++j) win[c][j] = pack2(w[j], w[j]);
     }
 
-    float* o = out + static_cast<size_t>(b) * F * L + l0;
+    float* o = out + (static_cast<size_t>(b) * F + 2 * static_cast<size_t>(p_begin)) * L + l0;
 #pragma unroll 2
-    for (int p = 0; p < pairs; ++p) {
+    for (int p = p_begin; p < p_end; ++p) {
         unsigned long long rec[PS / 2];                     // rec[i] = (w0[i], w1[i]); rec[P] = (shift0, shift1)
 #pragma unroll
         for (int i = 0; i < PS / 4; ++i) {
-            const float4 q = s_rec[p * (PS / 4) + i];
+            const float4 q = s_rec[(p - p_begin) * (PS / 4) + i];
             rec[2 * i + 0] = pack2(q.x, q.y);
             rec[2 * i + 1] = pack2(q.z, q.w);
         }
@@ -396,13 +398,25 @@ cudaError_t launch_for_channels(const float* x, const FoldArgs& fold_in, float* 
 
     const uint32_t quads_per_row = (static_cast<uint32_t>(L) + 3u) / 4u;
     const uint32_t total_quads = static_cast<uint32_t>(B) * quads_per_row;
-    const size_t smem = static_cast<size_t>((F + 1) / 2) * pair_stride(C) * sizeof(float);
     const bool vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
     const uint32_t blocks = (total_quads + kThreads - 1) / kThreads;
+    // a batch too small to fill the GPU with one CTA per 1024 positions (the reference's batch of 64: 157 CTAs) is also
+    // split along the filters, down to one filter pair per CTA
+    const int pairs = (F + 1) / 2;
+    const uint32_t fill = static_cast<uint32_t>(sm_count_of_current_device()) * 4u;
+    int groups = 1;
+    if (blocks < fill) {
+        const uint32_t want = (fill + blocks - 1) / blocks;
+        groups = want < static_cast<uint32_t>(pairs) ? static_cast<int>(want) : pairs;
+    }
+    const int per_group = (pairs + groups - 1) / groups;
+    groups = (pairs + per_group - 1) / per_group;
+    const size_t smem = static_cast<size_t>(per_group) * pair_stride(C) * sizeof(float);
+    const dim3 grid(blocks, static_cast<unsigned>(groups));
     if (vec)
-        apply_kernel<C, true><<<blocks, kThreads, smem, stream>>>(x, fold.records, out, total_quads, quads_per_row, static_cast<uint32_t>(L), F);
+        apply_kernel<C, true><<<grid, kThreads, smem, stream>>>(x, fold.records, out, total_quads, quads_per_row, static_cast<uint32_t>(L), F, per_group);
     else
-        apply_kernel<C, false><<<blocks, kThreads, smem, stream>>>(x, fold.records, out, total_quads, quads_per_row, static_cast<uint32_t>(L), F);
+        apply_kernel<C, false><<<grid, kThreads, smem, stream>>>(x, fold.records, out, total_quads, quads_per_row, static_cast<uint32_t>(L), F, per_group);
     return cudaGetLastError();
 }
 
