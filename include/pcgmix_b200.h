@@ -328,6 +328,9 @@ int pcgmix_cycle_moment_features(const float* x, const int32_t* frames, int32_t 
  *     until the stream has passed it.
  * Forward only (no gradient kernels).  float32 FMAs; agrees with torch's float32 modules to rounding (tests: 2e-5
  * relative + 2e-5 absolute on the output, 1e-5 relative on the statistics).  NaN propagates like torch's ReLU.
+ * The batch variance is formed from float32 products of raw samples summed in float64, so its relative error is about
+ * 1e-6 * (1 + mean^2 / variance) of the input: exact enough for band-passed, zero-centred heart-sound cycles (what the
+ * reference feeds it), not for inputs riding on a large constant offset.
  * Enqueues at most one memset and three kernels on `stream`; no allocation, no synchronisation.
  */
 long long pcgmix_first_conv_block_workspace(int32_t C, int32_t F);   /* bytes; -1 for unsupported sizes */
