@@ -47,12 +47,6 @@ __host__ __device__ constexpr int moment_count(int C) { return patch_len(C) + pa
 // a record holds TWO filters, interleaved: {w0[0], w1[0], w0[1], w1[1], ..., shift0, shift1}, padded to 128-bit units
 __host__ __device__ constexpr int pair_stride(int C) { return (2 * patch_len(C) + 2 + 3) & ~3; }  // floats
 
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
-    return v;
-}
-
 __device__ __forceinline__ float relu_nan(float v) {    // torch's ReLU keeps NaN; fmaxf would drop it
     float r;
     asm("max.NaN.f32 %0, %1, 0f00000000;" : "=f"(r) : "f"(v));
