@@ -94,6 +94,17 @@ def test_cpu_tensor_is_refused(golden):
         first_block.first_conv_block(_reference_block(g, "cpu"), torch.from_numpy(g["x"]))
 
 
+def test_workspace_size_is_a_host_side_query():
+    """No device needed: moments (3C + 3C(3C+1)/2 doubles, padded to 16 bytes) + one interleaved record per filter pair."""
+    from pcgmix_b200 import native
+    assert native.first_conv_block_workspace(4, 64) == 90 * 8 + 32 * 28 * 4
+    assert native.first_conv_block_workspace(1, 16) == 16 * ((9 * 8 + 15) // 16) + 8 * 8 * 4
+    assert native.first_conv_block_workspace(2, 7) == 16 * ((27 * 8 + 15) // 16) + 4 * 16 * 4        # odd filter count: 4 pairs
+    for bad in ((0, 8), (5, 8), (4, 0), (4, native.MAX_FIRST_BLOCK_FILTERS + 1)):
+        with pytest.raises(ValueError):
+            native.first_conv_block_workspace(*bad)
+
+
 def test_other_blocks_are_refused():
     from pcgmix_b200 import first_block
     pooled = torch.nn.Sequential(torch.nn.Conv1d(4, 8, 3, padding=1), torch.nn.BatchNorm1d(8), torch.nn.ReLU(), torch.nn.MaxPool1d(2))
